@@ -1,0 +1,391 @@
+"""Host prologue: everything ``run()`` does *before* the time loop, in torch fp64/complex128.
+
+This is the once-per-run part of the reference (SURVEY.md section 8b draws the kernel boundary after it):
+
+    admittance assembly      simulator.py:350-426   (+ branch formulas static_models.py:296-312, 397-413)
+    Newton-Raphson load flow load_flow.py:9-179
+    model initialisation     synchronous_machine.py:279-323, exciters.py:129-138, governors.py:136-145,
+                             stabilizers.py:135-145, blocks.py:196-207/332-342/426-436, static_models.py:515-527
+    Z = inv(Y_dyn), V = Z I  simulator.py:386, 447-450
+
+It is written with differentiable torch ops so the autograd graph from user leaf tensors
+(``gen.h = torch.tensor(..., requires_grad=True)``) to the kernel inputs exists; the step kernel's
+backward hands gradients w.r.t. those inputs back to this graph.
+
+Batch handling.  Every quantity is a ``[B,1]`` tensor with ``B in {1, P}``: attributes that are identical in
+every sim are collapsed to one row (broadcasting does the rest), so the load flow and the matrix inverse run
+once when the network is shared by the batch and per sim when somebody varies ``x_d_st``, a load, ...
+The collapse doubles as the kernel's uniform / per-sim classification of its inputs.
+
+Two reference quirks are inherited deliberately because parity is judged against the reference's torch path:
+  * line / transformer parameters are read from the **last** sim only.  The reference turns bus indices into
+    ``[P,1]`` index tensors (static_models.py:321-322), so ``Y[:, from, to] += v`` (simulator.py:367-380)
+    scatters with duplicate indices and the last row wins for every sim (and costs O(P^2) there).
+  * the load flow stops when ``max |mismatch| < 1e-8`` over the *whole batch*, after applying one more
+    update (load_flow.py:147-167).
+"""
+import math
+
+import torch
+
+from .components import SynchMachine, Load, Shunt
+
+C128 = torch.complex128
+F64 = torch.float64
+
+# ---- kernel-level per-generator constants ("slots"); order is part of the C ABI (include/dps.h) -------------
+SLOTS = (
+    # machine (synchronous_machine.py:158-164, 256-277)
+    'inv_2h', 'd', 'inv_td0t', 'xd_xdt', 'inv_tq0t', 'xq_xqt', 'inv_td0st', 'xdt_xdst', 'inv_tq0st', 'xqt_xqst',
+    'inv_xdst', 'inv_xqst', 'snr', 'pm0', 'efd0',
+    # SEXS (exciters.py:102-115; blocks.py:143-150, 290, 319)
+    'a_r', 'a_omr', 'a_inv_tb', 'a_inv_te', 'a_k', 'a_emin', 'a_emax', 'a_vset', 'a_bias',
+    # TGOV1 (governors.py:105-123)
+    'g_inv_t1', 'g_gain', 'g_vmin', 'g_vmax', 'g_r', 'g_omr', 'g_inv_t3', 'g_dt', 'g_pref',
+    # STAB1 (stabilizers.py:106-121; blocks.py:382, 413, 241)
+    's_inv_tw', 's_kw', 's_r1', 's_omr1', 's_inv_t3', 's_r2', 's_omr2', 's_inv_t4', 's_hlim',
+)
+SLOT_INDEX = {n: i for i, n in enumerate(SLOTS)}
+N_SLOTS = len(SLOTS)
+
+CTRL_AVR, CTRL_GOV, CTRL_PSS = 1, 2, 4
+
+
+class _Cols(object):
+    """Fetches model attributes as ``[B,1]`` tensors on the run device, collapsing batch-uniform ones."""
+
+    def __init__(self, P, device):
+        self.P, self.device = P, device
+
+    def __call__(self, value, dtype=None, collapse=True, last_row=False):
+        P = self.P
+        if not torch.is_tensor(value):
+            dt = dtype or (C128 if isinstance(value, complex) else F64)
+            return torch.full((1, 1), value, dtype=dt, device=self.device)
+        t = value
+        if t.device != torch.device(self.device):
+            t = t.to(self.device)
+        if t.dim() == 0:
+            t = t.reshape(1, 1)
+        elif t.dim() == 1:
+            t = t.reshape(-1, 1)
+        if dtype is not None and t.dtype != dtype:
+            if t.is_complex() and not dtype.is_complex:
+                t = t.real
+            t = t.to(dtype)
+        if last_row:
+            return t[-1:]
+        if collapse and t.shape[0] == P and P > 1 and not t.requires_grad:
+            if bool((t == t[:1]).all()):
+                return t[:1]
+        return t
+
+
+def _real(t):
+    return t.real if t.is_complex() else t
+
+
+def generators_of(sim):
+    """Generators in the order the reference's solver visits them: bus order, then model order
+    (solvers.py:84-86)."""
+    out = []
+    for bi, bus in enumerate(sim.busses):
+        for m in bus.models:
+            if isinstance(m, SynchMachine):
+                out.append((bi, m))
+    return out
+
+
+# ==================================================================================================
+# admittance matrices
+# ==================================================================================================
+def _branch_terms(sim, col):
+    """(from, to, y_off, y_diag) per branch, in the reference's accumulation order: lines, then transformers."""
+    terms = []
+    for ln in sim.lines:
+        r, x, b = (col(v, F64, last_row=True) for v in (ln.r, ln.x, ln.b))
+        series = 1 / (r + 1j * x)
+        terms.append((ln.from_bus_id, ln.to_bus_id, -series, series + 1j * b / 2))
+    for tr in sim.trafos:
+        r, x = (col(v, F64, last_row=True) for v in (tr.r, tr.x))
+        series = 1 / (r + 1j * x)
+        ratio_num, ratio_den = tr.s_n, tr.s_n_sys
+        terms.append((tr.from_bus_id, tr.to_bus_id,
+                      -series * ratio_num / ratio_den, (series + 1j * tr.b / 2) * ratio_num / ratio_den))
+    return terms
+
+
+def _assemble(sim, col, diag_contrib):
+    """Y[B,n,n] = branches + per-bus diagonal contributions (simulator.py:362-384 / 400-422).
+    Built out-of-place so autograd sees every contribution."""
+    n = len(sim.busses)
+    entries = {}
+
+    def add(i, j, v):
+        v = v.reshape(-1).to(C128)
+        entries[(i, j)] = v if (i, j) not in entries else entries[(i, j)] + v
+
+    for f, t, y_off, y_diag in _branch_terms(sim, col):
+        add(f, t, y_off)
+        add(t, f, y_off)
+        add(f, f, y_diag)
+        add(t, t, y_diag)
+    for i, contribs in enumerate(diag_contrib):
+        for v in contribs:
+            add(i, i, v)
+    B = max([v.shape[0] for v in entries.values()] + [1])
+    zero = torch.zeros(B, dtype=C128, device=col.device)
+    rows = []
+    for i in range(n):
+        rows.append(torch.stack([entries[(i, j)].expand(B) if (i, j) in entries else zero for j in range(n)],
+                                dim=-1))
+    return torch.stack(rows, dim=-2)
+
+
+def static_admittance(sim, col):
+    """Load-flow admittance: branches + shunts (generators and loads contribute zero, static_models.py:497-513,
+    synchronous_machine.py:337-338)."""
+    diag = []
+    for bus in sim.busses:
+        diag.append([col(m.y_shunt, C128) for m in bus.models if isinstance(m, Shunt)])
+    return _assemble(sim, col, diag)
+
+
+def dynamic_admittance(sim, col):
+    """Dynamic admittance: branches + shunts + constant-Z loads + generator Norton admittances
+    ``-j/x_d'' * S_n/S_sys`` (synchronous_machine.py:336)."""
+    diag = []
+    for bus in sim.busses:
+        c = []
+        for m in bus.models:
+            if isinstance(m, Shunt):
+                c.append(col(m.y_shunt, C128))
+            elif isinstance(m, Load):
+                c.append(m.y_load)
+            elif isinstance(m, SynchMachine):
+                c.append(-1j / col(m.x_d_st, C128) * (col(m.s_n, C128) / m.s_n_sys))
+        diag.append(c)
+    return _assemble(sim, col, diag)
+
+
+# ==================================================================================================
+# load flow
+# ==================================================================================================
+def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
+    """Polar Newton-Raphson power flow, batched over B.  Same unknown ordering, update sequence and stopping
+    rule as load_flow.py:37-170.  Returns (V[B,n], S_calc[B,n], iterations)."""
+    n = len(sim.busses)
+    dev = col.device
+    pv = [i for i, b in enumerate(sim.busses) if b.lf_type == 'PV']
+    pq = [i for i, b in enumerate(sim.busses) if b.lf_type == 'PQ']
+    ang_ids = pv + pq                                  # angle unknowns / P equations
+    n_ang = len(ang_ids)
+
+    # scheduled injections (static_models.py:165-176; synchronous_machine.py:347; static_models.py:495)
+    s_parts = []
+    for bus in sim.busses:
+        s = torch.zeros((1, 1), dtype=C128, device=dev)
+        for m in bus.models:
+            if isinstance(m, SynchMachine):
+                s = s + (col(m.p_soll_mw, C128) + 1j * 0) / m.s_n_sys
+            elif isinstance(m, Load):
+                s = s + (-(col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys)
+        s_parts.append(s)
+    v_parts = [col(b.voltage, C128) for b in sim.busses]
+    B = max([y_bus.shape[0]] + [s.shape[0] for s in s_parts] + [v.shape[0] for v in v_parts])
+    s_soll = torch.cat([s.expand(B, 1) for s in s_parts], dim=1)              # [B,n]
+    V = torch.cat([v.expand(B, 1) for v in v_parts], dim=1)                   # [B,n]
+    G, Bm = y_bus.real, y_bus.imag
+    ia = torch.tensor(ang_ids, device=dev, dtype=torch.long)
+    iq = torch.tensor(pq, device=dev, dtype=torch.long)
+    eye_a = torch.eye(n_ang, dtype=torch.bool, device=dev)
+    it = 0
+    while True:
+        s_calc = V * torch.conj(torch.matmul(y_bus, V.unsqueeze(-1)).squeeze(-1))
+        th, vm = torch.angle(V), torch.abs(V)
+        dth = th.unsqueeze(2) - th.unsqueeze(1)                               # theta_i - theta_k
+        sin, cos = torch.sin(dth), torch.cos(dth)
+        a = G * sin - Bm * cos
+        c = G * cos + Bm * sin
+        vi, vk = vm.unsqueeze(2), vm.unsqueeze(1)
+        Pc, Qc = s_calc.real, s_calc.imag
+        Gd = torch.diagonal(G, dim1=1, dim2=2)
+        Bd = torch.diagonal(Bm, dim1=1, dim2=2)
+        # J holds minus the usual Jacobian, exactly as load_flow.py:75-140 builds it
+        J11 = -vi * vk * a
+        J11 = torch.where(torch.eye(n, dtype=torch.bool, device=dev), (vm ** 2 * Bd + Qc).unsqueeze(2).expand(B, n, n), J11)
+        J12 = -vi * c
+        J12 = torch.where(torch.eye(n, dtype=torch.bool, device=dev), (-vm * Gd - Pc / vm).unsqueeze(2).expand(B, n, n), J12)
+        J21 = vi * vk * c
+        J21 = torch.where(torch.eye(n, dtype=torch.bool, device=dev), (vm ** 2 * Gd - Pc).unsqueeze(2).expand(B, n, n), J21)
+        J22 = -vi * a
+        J22 = torch.where(torch.eye(n, dtype=torch.bool, device=dev), (vm * Bd - Qc / vm).unsqueeze(2).expand(B, n, n), J22)
+        top = torch.cat([J11[:, ia][:, :, ia], J12[:, ia][:, :, iq]], dim=2)
+        bot = torch.cat([J21[:, iq][:, :, ia], J22[:, iq][:, :, iq]], dim=2)
+        J = torch.cat([top, bot], dim=1)
+        err = s_calc - s_soll
+        rhs = torch.cat([err.real[:, ia], err.imag[:, iq]], dim=1).unsqueeze(-1)
+        dx = torch.linalg.solve(-J, rhs).squeeze(-1)                           # [B, n_ang + n_pq]
+        # update: angles of PV and PQ buses, then magnitudes of PQ buses (load_flow.py:150-158)
+        cols = [V[:, i] for i in range(n)]
+        for k, b in enumerate(ang_ids):
+            v = cols[b]
+            cols[b] = torch.abs(v) * torch.exp(1j * (torch.angle(v) - dx[:, k]))
+        for k, b in enumerate(pq):
+            v = cols[b]
+            cols[b] = (torch.abs(v) - dx[:, n_ang + k]) * torch.exp(1j * torch.angle(v))
+        V = torch.stack(cols, dim=1)
+        worst = float(torch.max(torch.abs(rhs)))
+        if worst < tol:
+            break
+        if it > max_iter:
+            raise ValueError('Load flow did not converge')
+        it += 1
+    del eye_a
+    s_calc = V * torch.conj(torch.matmul(y_bus, V.unsqueeze(-1)).squeeze(-1))
+    return V, s_calc, it
+
+
+# ==================================================================================================
+# model initialisation -> kernel inputs
+# ==================================================================================================
+class InitResult(object):
+    """What the time loop consumes."""
+    __slots__ = ('gens', 'gen_bus', 'ctrl', 'x0', 'slots', 'Z0', 'Ydiag', 'bus_v', 's_calc', 'lf_iters',
+                 'omega_scale')
+
+
+def _clamp(x, lo, hi):
+    return torch.minimum(torch.maximum(x, lo), hi)
+
+
+def initialize(sim, device):
+    """Load flow + model initialisation + Z = inv(Y_dyn) + initial bus voltages.
+    Mirrors simulator.py:438-450.  Everything returned is ``[B,1]`` (B in {1,P}) real float64, except Z0/Ydiag/bus_v."""
+    P = sim.parallel_sims
+    col = _Cols(P, device)
+    res = InitResult()
+    y_static = static_admittance(sim, col)
+    V, s_calc, iters = load_flow(sim, col, y_static)
+    res.lf_iters = iters
+    res.s_calc = s_calc
+
+    gens = generators_of(sim)
+    res.gens = [g for _, g in gens]
+    res.gen_bus = [bi for bi, _ in gens]
+    res.ctrl, res.x0, res.slots = [], [], []
+    res.omega_scale = None
+
+    # loads become constant admittances from the load-flow voltage (static_models.py:515-527)
+    for bi, bus in enumerate(sim.busses):
+        v_bb = V[:, bi:bi + 1]
+        for m in bus.models:
+            if isinstance(m, Load):
+                s_load = (col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys
+                z_load = torch.conj(torch.abs(v_bb) ** 2 / s_load)
+                m.y_load = 1 / z_load
+
+    for bi, g in gens:
+        v_bb = V[:, bi:bi + 1]
+        s_bus = s_calc[:, bi:bi + 1]
+        c = {k: col(getattr(g, k), C128) for k in ('s_n', 'h', 'd', 'x_d', 'x_q', 'x_d_t', 'x_q_t', 'x_d_st', 'x_q_st',
+                                                   't_d0_t', 't_q0_t', 't_d0_st', 't_q0_st')}
+        snr = c['s_n'] / g.s_n_sys
+        # synchronous_machine.py:290-314
+        i_gen = torch.conj(s_bus / v_bb) / snr
+        e = v_bb + 1j * c['x_q'] * i_gen
+        delta = torch.angle(e)
+        rot = torch.exp(1j * (math.pi / 2 - delta))
+        i_dq = i_gen * rot
+        i_d, i_q = i_dq.real, i_dq.imag
+        v_dq = v_bb * rot
+        v_d, v_q = v_dq.real, v_dq.imag
+        e_q_t = v_q + c['x_d_t'] * i_d
+        e_d_t = v_d - c['x_q_t'] * i_q
+        e_q_st = v_q + c['x_d_st'] * i_d
+        e_d_st = v_d - c['x_q_st'] * i_q
+        p_m = s_bus.real / snr
+        e_fd = e_q_t + i_d * (c['x_d'] - c['x_d_t'])
+
+        x0 = [torch.zeros_like(delta), delta, _real(e_q_t), _real(e_d_t), _real(e_q_st), _real(e_d_st)]
+        sl = {
+            'inv_2h': _real(1 / (2 * c['h'])), 'd': _real(c['d']),
+            'inv_td0t': _real(1 / c['t_d0_t']), 'xd_xdt': _real(c['x_d'] - c['x_d_t']),
+            'inv_tq0t': _real(1 / c['t_q0_t']), 'xq_xqt': _real(c['x_q'] - c['x_q_t']),
+            'inv_td0st': _real(1 / c['t_d0_st']), 'xdt_xdst': _real(c['x_d_t'] - c['x_d_st']),
+            'inv_tq0st': _real(1 / c['t_q0_st']), 'xqt_xqst': _real(c['x_q_t'] - c['x_q_st']),
+            'inv_xdst': _real(1 / c['x_d_st']), 'inv_xqst': _real(1 / c['x_q_st']),
+            'snr': _real(snr), 'pm0': _real(p_m), 'efd0': _real(e_fd),
+        }
+        flags = 0
+        if g.exciter:
+            flags |= CTRL_AVR
+            ex = g.exciter
+            ll, pt = ex.lead_lag, ex.pt1_lim
+            t_a, t_b = col(ll.t_1, None), col(ll.t_2, None)
+            t_e, k = col(pt.t_pt1, None), col(pt.gain_pt1, None)
+            emin, emax = col(pt.lim_min, None), col(pt.lim_max, None)
+            # blocks.py:206-207 then 341-342 via exciters.py:137-138
+            x_pt = _clamp(_real(e_fd), _real(emin), _real(emax))
+            bias = e_fd / k
+            x0 += [_real(bias), x_pt]
+            r = t_a / t_b
+            sl.update({'a_r': _real(r), 'a_omr': _real(1 - r), 'a_inv_tb': _real(1 / t_b), 'a_inv_te': _real(1 / t_e),
+                       'a_k': _real(k), 'a_emin': _real(emin), 'a_emax': _real(emax),
+                       'a_vset': _real(col(ex.v_setpoint, None)), 'a_bias': _real(bias)})
+            ex.bias = bias
+        if g.governor:
+            flags |= CTRL_GOV
+            gv = g.governor
+            pt, ll = gv.pt1_lim, gv.lead_lag
+            t_1, gain = col(pt.t_pt1, None), col(pt.gain_pt1, None)
+            vmin, vmax = col(pt.lim_min, None), col(pt.lim_max, None)
+            t_2, t_3 = col(ll.t_1, None), col(ll.t_2, None)
+            # governors.py:144-145: lead-lag state = p_m; PT1 state = clamp(p_m); p_ref = p_m / gain
+            x_pt = _clamp(_real(p_m), _real(vmin), _real(vmax))
+            p_ref = p_m / gain
+            x0 += [x_pt, _real(p_m)]
+            r = t_2 / t_3
+            sl.update({'g_inv_t1': _real(1 / t_1), 'g_gain': _real(gain), 'g_vmin': _real(vmin), 'g_vmax': _real(vmax),
+                       'g_r': _real(r), 'g_omr': _real(1 - r), 'g_inv_t3': _real(1 / t_3),
+                       'g_dt': _real(col(gv.d_t, None)), 'g_pref': _real(p_ref)})
+            gv.p_ref = p_ref
+        if g.stabilizer:
+            flags |= CTRL_PSS
+            st = g.stabilizer
+            k_w, t_w = col(st.washout.k_w, None), col(st.washout.t_w, None)
+            t1, t3 = col(st.lead_lag1.t_1, None), col(st.lead_lag1.t_2, None)
+            t2, t4 = col(st.lead_lag2.t_1, None), col(st.lead_lag2.t_2, None)
+            # synchronous_machine.py:323 initialises the PSS with e_fd*0 -> all three states zero
+            # (blocks.py:341, 435: washout state = k_w * 0)
+            z = _real(e_fd) * 0
+            x0 += [_real(k_w * (e_fd * 0)), z, z]
+            r1, r2 = t1 / t3, t2 / t4
+            sl.update({'s_inv_tw': _real(1 / t_w), 's_kw': _real(k_w), 's_r1': _real(r1), 's_omr1': _real(1 - r1),
+                       's_inv_t3': _real(1 / t3), 's_r2': _real(r2), 's_omr2': _real(1 - r2),
+                       's_inv_t4': _real(1 / t4), 's_hlim': _real(col(st.limiter.limit, None))})
+        res.ctrl.append(flags)
+        res.x0.append(x0)
+        res.slots.append(sl)
+        # expose initial values on the container, as the reference does
+        g.omega, g.delta = torch.zeros_like(e), delta.to(C128) if not delta.is_complex() else delta
+        g.e_q_t, g.e_d_t, g.e_q_st, g.e_d_st = e_q_t, e_d_t, e_q_st, e_d_st
+        g.p_m, g.e_fd = p_m, e_fd
+
+    y_dyn = dynamic_admittance(sim, col)
+    res.Ydiag = torch.diagonal(y_dyn, dim1=1, dim2=2)
+    res.Z0 = torch.linalg.inv(y_dyn)
+    res.bus_v = V
+    return res
+
+
+def initial_injections(res, device):
+    """Norton current injections of every generator at x0 (synchronous_machine.py:256-260), [B,G] complex."""
+    cur = []
+    for x0, sl in zip(res.x0, res.slots):
+        delta, eq, ed = x0[1], x0[4], x0[5]
+        i_d = eq / (1j / sl['inv_xdst']) * torch.exp(1j * delta)
+        i_q = ed / (1j / sl['inv_xqst']) * torch.exp(1j * (delta - math.pi / 2))
+        cur.append((i_d + i_q) * sl['snr'])
+    B = max(c.shape[0] for c in cur)
+    return torch.cat([c.expand(B, 1) for c in cur], dim=1)

@@ -1,0 +1,267 @@
+"""TEST INFRASTRUCTURE -- generates the fixtures under tests/golden/ (run in the build container only).
+
+    python oracle/gen_golden.py            # everything (a few minutes on 8 cores)
+    python oracle/gen_golden.py k2a        # cases whose name contains 'k2a'
+
+It imports the unmodified reference from /root/reference through ``oracle/ref_harness.py`` with the
+reference's *torch* backend (the path parity is judged against, BASELINE.json north_star) and stores
+
+  tests/golden/grids/<grid>.json      the example grid dicts (reference: examples/models/*/*_model.py ``load()``)
+  tests/golden/ref_<name>.npy         copies of the reference's own golden arrays
+                                      (reference: tests/integration/data/*.npy, made by its numpy backend)
+  tests/golden/<case>.npz             live torch-backend outputs: snapshot after initialize(), every state /
+                                      algebraic / bus voltage at a subset of steps (all steps around the fault),
+                                      the example's own record channels at every step, and for ``grad_*`` cases
+                                      the autograd gradients of a per-sim MSE loss.
+
+``/root/reference`` does not exist on the GPU box; tests read only the committed fixtures.
+"""
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+GRIDS = {
+    'ibb': ('ibb_model', 'ibb_model'),
+    'ibb_trans': ('ibb_transformer', 'ibb_trans_model'),
+    'ibb_wc': ('ibb_with_controllers', 'ibb_wc_model'),
+    'ieee9': ('ieee_9bus', 'ieee_9bus_model'),
+    'k2a': ('k2a', 'k2a_model'),
+}
+
+# (grid, sim_time, events, reference golden file, record channels of the example's *_sim.py)
+EXAMPLES = {
+    'ibb': (10, [(1, 1.05, 'Bus 1')], 'ibb_model',
+            ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st']),                     # ibb_sim.py:20-24,41
+    'ibb_trans': (10, [(1, 1.05, 'Bus 0')], 'ibb_transformer',
+                  ['G2.omega', 'G2.e_q_st', 'G2.e_d_st']),                        # ibb_trans_sim.py:20-24,41
+    'ibb_wc': (10, [(1, 1.05, 'B2')], 'ibb_with_controllers',
+               ['G1.omega']),                                                     # golden holds omega only
+    'ieee9': (5, [(1, 1.05, 'B8')], 'ieee_9bus',
+              ['G1.omega', 'G1.p_e', 'G1.v_re', 'G1.v_im',
+               'G2.omega', 'G2.p_e', 'bus:B2.v_re', 'bus:B2.v_im',
+               'G3.omega', 'G3.p_e', 'bus:B3.v_re', 'bus:B3.v_im']),              # ieee_9bus_sim.py:20-36,52
+    'k2a': (10, [(1, 1.1, 'B1')], 'k2a',
+            ['G%d.%s' % (g, s) for s in ('delta', 'omega', 'e_q_st', 'e_d_st') for g in (1, 2, 3, 4)]),
+}
+
+DT = 0.005
+
+
+def keep_steps(T, events, stride=5, pad=12):
+    """Steps stored for the all-channel trajectory: every ``stride``-th, the first 3, the last, and every step
+    from ``pad`` before a fault to ``pad`` after it."""
+    keep = set(range(0, T, stride)) | {0, 1, 2, T - 1}
+    for (t0, t1, _b) in events:
+        a = int(round(t0 / DT)) - pad
+        b = int(round(t1 / DT)) + pad
+        keep |= set(range(max(a, 0), min(b, T)))
+    return np.array(sorted(keep), dtype=np.int64)
+
+
+def save_case(name, t, rec, names, snap, events, solver, extra=None, stride=5):
+    T = rec.shape[1]
+    steps = keep_steps(T, events, stride=stride)
+    out = {
+        'steps': steps,
+        'traj': rec[:, steps, :],                  # [P, n_keep, C]
+        'names': np.array(names),
+        'time': t,
+        'solver': np.array(solver),
+        'events': np.array(json.dumps(events)),
+    }
+    for k, v in snap.items():
+        out['init/' + k] = v
+    if extra:
+        out.update(extra)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **out)
+    print('wrote', name, 'P=%d T=%d C=%d kept=%d' % (rec.shape[0], T, rec.shape[2], len(steps)))
+
+
+def example_cases(sel):
+    for gname, (sim_time, events, ref_file, chans) in EXAMPLES.items():
+        grid = rh.load_example_grid(*GRIDS[gname])
+        for solver in ('heun', 'euler', 'rk4'):
+            name = '%s_%s' % (gname, solver)
+            if sel and not any(s in name for s in sel):
+                continue
+            sim, _ = rh.build(grid, 1, solver, DT, sim_time, events)
+            t, rec, names, snap, _ = rh.run_full(sim)
+            idx = [names.index(c) for c in chans]
+            extra = {'example_channels': np.array(chans), 'example_rec': rec[0][:, idx]}
+            if solver == 'heun':
+                ref = np.load(os.path.join(rh.REFERENCE_ROOT, 'tests', 'integration', 'data', ref_file + '.npy'))
+                d = np.abs(ref - rec[0][:, idx]).max()
+                print('   torch-vs-reference-golden(%s) max|diff| = %.3e' % (ref_file, d))
+                assert d < 1e-6      # the reference's own tolerance, tests/integration/test_example_sims.py:18-19
+            save_case(name, t, rec, names, snap, events, solver, extra)
+
+
+def batch_cases(sel):
+    rng = np.random.RandomState(0)
+    # --- K2A, per-sim H / D / X_d' on every generator, narrow (stable) range, plus PSS gains on G1
+    name = 'k2a_batch_heun'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['k2a'])
+        P = 6
+        nominal = {'h': [6.5, 6.5, 6.175, 6.175], 'x_d_t': [0.3] * 4}
+        ov = {}
+        for gi in range(4):
+            gn = 'G%d' % (gi + 1)
+            ov[('gen', gn, 'h')] = nominal['h'][gi] * rng.uniform(0.9, 1.1, P)
+            ov[('gen', gn, 'd')] = rng.uniform(0.0, 2.0, P)
+            ov[('gen', gn, 'x_d_t')] = nominal['x_d_t'][gi] * rng.uniform(0.9, 1.1, P)
+        ov[('gen', 'G1', 'stabilizer.washout.k_w')] = 50.0 * rng.uniform(0.5, 2.0, P)
+        ov[('gen', 'G2', 'exciter.pt1_lim.gain_pt1')] = 100.0 * rng.uniform(0.8, 1.2, P)
+        events = [(1, 1.1, 'B1')]
+        sim, _ = rh.build(grid, P, 'heun', DT, 4, events, ov)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        save_case(name, t, rec, names, snap, events, 'heun', extra)
+    # --- IBB, the reference's own 0.5x..2x identification range (ibb_opt.py:48-57); contains unstable rows
+    name = 'ibb_batch_heun'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['ibb'])
+        P = 8
+        ov = {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.5, 2.0, P),
+              ('gen', 'Gen 1', 'd'): rng.uniform(0.0, 2.0, P),
+              ('gen', 'Gen 1', 'x_d_t'): 0.3 * rng.uniform(0.5, 2.0, P)}
+        events = [(1, 1.05, 'Bus 1')]
+        sim, _ = rh.build(grid, P, 'heun', DT, 10, events, ov)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        save_case(name, t, rec, names, snap, events, 'heun', extra)
+    # --- per-sim network: x_d_st (enters Y, synchronous_machine.py:336) varied -> per-sim Z path
+    name = 'ieee9_persimz_heun'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['ieee9'])
+        P = 4
+        ov = {('gen', 'G2', 'x_d_st'): 0.2 * rng.uniform(0.8, 1.2, P),
+              ('gen', 'G3', 'h'): 2.766544 * rng.uniform(0.8, 1.2, P)}
+        events = [(1, 1.05, 'B8')]
+        sim, _ = rh.build(grid, P, 'heun', DT, 3, events, ov)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        save_case(name, t, rec, names, snap, events, 'heun', extra)
+    # --- two overlapping / cancelling events: pins the `else` quirk of simulator.py:524-531
+    name = 'ieee9_two_events_heun'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['ieee9'])
+        events = [(0.5, 0.6, 'B8'), (0.55, 0.7, 'B5')]
+        sim, _ = rh.build(grid, 1, 'heun', DT, 2, events)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        save_case(name, t, rec, names, snap, events, 'heun', stride=1)
+    name = 'k2a_two_events_rk4'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['k2a'])
+        events = [(0.2, 0.3, 'B7'), (0.1, 0.25, 'B1')]
+        sim, _ = rh.build(grid, 1, 'rk4', DT, 1.5, events)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        save_case(name, t, rec, names, snap, events, 'rk4', stride=1)
+
+
+def grad_cases(sel):
+    """Gradient known-answer vectors.  The reference's tests pin no gradient values
+    (tests/integration/test_example_opts.py asserts nothing), so these come from the reference's own
+    autograd (``loss.sum().backward()``, ps_optimization.py:212) and are cross-checked here by central
+    finite differences on the reference itself."""
+    import torch
+    rng = np.random.RandomState(1)
+
+    def one(name, gname, P, solver, sim_time, events, ov, chans, fd_check):
+        if sel and not any(s in name for s in sel):
+            return
+        grid = rh.load_example_grid(*GRIDS[gname])
+        ref_traj = np.load(os.path.join(GOLD, '%s_%s.npz' % (gname, 'heun')))
+        all_names = list(ref_traj['names'])
+
+        def run(ovv, grad):
+            sim, leaves = rh.build(grid, P, solver, DT, sim_time, events, ovv, requires_grad=grad)
+            t, rec, names, snap, rec_t = rh.run_full(sim)
+            idx = [names.index(c) for c in chans]
+            return sim, leaves, rec_t[:, :, idx], names, snap, t, rec
+
+        sim, leaves, out, names, snap, t, rec = run(ov, True)
+        T = out.shape[1]
+        # target: a smooth synthetic signal (deterministic) so the loss is O(1e-3) and well conditioned
+        tt = torch.tensor(t)[None, :, None]
+        target = 0.002 * torch.sin(2.0 * tt) * torch.ones_like(out.real)
+        loss = ((out.real - target) ** 2).mean(dim=(1, 2))          # [P]
+        loss.sum().backward()
+        grads = {k: v.grad.real.numpy().reshape(-1).copy() for k, v in leaves.items()}
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        extra.update({'grad/' + '|'.join(k): v for k, v in grads.items()})
+        extra['loss'] = loss.detach().numpy()
+        extra['loss_channels'] = np.array(chans)
+        extra['target'] = target[0, :, 0].numpy()
+        # finite-difference cross-check of the oracle's own gradients (one parameter, all sims at once: rows
+        # are independent so a simultaneous perturbation of every row gives every row's derivative)
+        if fd_check:
+            k0 = list(ov.keys())[0]
+            h = 1e-6 * np.abs(ov[k0]).max()
+            lp = []
+            for sgn in (+1, -1):
+                ov2 = dict(ov)
+                ov2[k0] = ov[k0] + sgn * h
+                _, _, o2, _, _, _, _ = run(ov2, False)
+                lp.append(((o2.real - target) ** 2).mean(dim=(1, 2)).numpy())
+            fd = (lp[0] - lp[1]) / (2 * h)
+            rel = np.abs(fd - grads[k0]) / (np.abs(grads[k0]) + 1e-30)
+            print('   FD check on %s: max rel diff %.2e' % ('|'.join(k0), rel.max()))
+            extra['fd/' + '|'.join(k0)] = fd
+        save_case(name, t, rec, names, snap, events, solver, extra, stride=20)
+
+    P = 4
+    one('grad_ibb_heun', 'ibb', P, 'heun', 2.0, [(1, 1.05, 'Bus 1')],
+        {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.8, 1.5, P),
+         ('gen', 'Gen 1', 'd'): rng.uniform(0.5, 2.0, P),
+         ('gen', 'Gen 1', 'x_d_t'): 0.3 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'Gen 1', 'x_q'): 1.76 * rng.uniform(0.8, 1.25, P)},
+        ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], True)
+    one('grad_ibb_euler', 'ibb', P, 'euler', 1.5, [(1, 1.05, 'Bus 1')],
+        {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.8, 1.5, P),
+         ('gen', 'Gen 1', 'x_d'): 1.81 * rng.uniform(0.8, 1.25, P)},
+        ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], False)
+    one('grad_ibb_rk4', 'ibb', P, 'rk4', 1.5, [(1, 1.05, 'Bus 1')],
+        {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.8, 1.5, P),
+         ('gen', 'Gen 1', 't_d0_t'): 8.0 * rng.uniform(0.8, 1.25, P)},
+        ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], False)
+    P = 3
+    # H_lim is raised to 0.3 so the PSS works in its linear range part of the time (with the stock 0.03 it is
+    # clamped for the whole post-fault window and every PSS gradient is exactly zero).
+    one('grad_k2a_heun', 'k2a', P, 'heun', 2.0, [(0.1, 0.13, 'B1')],
+        {('gen', 'G1', 'stabilizer.washout.k_w'): 50.0 * rng.uniform(0.5, 2.0, P),
+         ('gen', 'G1', 'stabilizer.lead_lag1.t_1'): 0.5 * rng.uniform(0.5, 2.0, P),
+         ('gen', 'G1', 'stabilizer.limiter.limit'): 0.3 * np.ones(P),
+         ('gen', 'G2', 'h'): 6.5 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'G3', 'exciter.pt1_lim.gain_pt1'): 100.0 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'G4', 'governor.lead_lag.t_1'): 1.0 * rng.uniform(0.8, 1.25, P)},
+        ['G%d.omega' % g for g in (1, 2, 3, 4)] + ['G1.e_q_st', 'G3.e_d_st'], True)
+
+
+def main():
+    sel = sys.argv[1:]
+    os.makedirs(os.path.join(GOLD, 'grids'), exist_ok=True)
+    for gname, (ex, mod) in GRIDS.items():
+        with open(os.path.join(GOLD, 'grids', gname + '.json'), 'w') as f:
+            json.dump(rh.load_example_grid(ex, mod), f, indent=1)
+    for ref in ('ibb_model', 'ibb_transformer', 'ibb_with_controllers', 'ieee_9bus', 'k2a'):
+        shutil.copyfile(os.path.join(rh.REFERENCE_ROOT, 'tests', 'integration', 'data', ref + '.npy'),
+                        os.path.join(GOLD, 'ref_' + ref + '.npy'))
+        os.chmod(os.path.join(GOLD, 'ref_' + ref + '.npy'), 0o644)
+    example_cases(sel)
+    batch_cases(sel)
+    grad_cases(sel)
+
+
+if __name__ == '__main__':
+    main()
