@@ -1,0 +1,222 @@
+// dps_abi.cu -- extern "C" entry points declared in include/dps.h (host code; no torch types).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "dps_internal.h"
+
+namespace dps {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+}  // namespace dps
+
+using namespace dps;
+
+struct dps_plan {
+    dps_topology topo;                    // scalar members valid; pointers re-targeted to the vectors below
+    std::vector<int32_t> ctrl;
+    std::vector<uint8_t> step_cfg;
+    std::vector<int32_t> slot_vary;
+    std::vector<dps_channel> rec;
+    std::vector<int> seg_step, seg_cfg;   // configuration change points
+    int g_template;
+    bool any_ctrl, any_vary;
+    FwdParams base;                       // everything that does not depend on the call
+};
+
+extern "C" {
+
+const char* dps_last_error(void) { return g_error.c_str(); }
+int dps_abi_version(void) { return DPS_ABI_VERSION; }
+
+int dps_plan_create(const dps_topology* t, dps_plan** out) {
+    if (!t || !out) { set_error("dps_plan_create: null argument"); return 1; }
+    if (t->abi_version != DPS_ABI_VERSION) { set_error("dps_plan_create: ABI version %d != %d", t->abi_version, DPS_ABI_VERSION); return 1; }
+    if (t->n_gen < 1) { set_error("dps_plan_create: n_gen must be >= 1"); return 1; }
+    if (t->n_gen > MAX_G) {
+        set_error("dps_plan_create: %d generators exceed the register-resident stepper limit (%d)", t->n_gen, MAX_G);
+        return 2;
+    }
+    if (t->solver < DPS_EULER || t->solver > DPS_RK4) { set_error("dps_plan_create: unknown solver %d", t->solver); return 1; }
+    if (t->n_steps < 0 || !(t->dt > 0.0)) { set_error("dps_plan_create: bad n_steps/dt"); return 1; }
+    if (t->n_obs < t->n_gen || t->n_obs - t->n_gen > MAX_EXTRA_OBS) { set_error("dps_plan_create: n_obs out of range"); return 1; }
+    if (t->z_rows < t->n_obs || t->z_cols < t->n_gen) { set_error("dps_plan_create: z_rows/z_cols smaller than n_obs/n_gen"); return 1; }
+    if (t->n_cfg < 1) { set_error("dps_plan_create: n_cfg must be >= 1"); return 1; }
+    if (t->n_rec < 0 || t->n_rec > 32000) { set_error("dps_plan_create: n_rec out of range"); return 1; }
+
+    dps_plan* pl = new dps_plan();
+    pl->topo = *t;
+    pl->ctrl.assign(t->ctrl, t->ctrl + t->n_gen);
+    pl->step_cfg.assign(t->step_cfg, t->step_cfg + t->n_steps);
+    pl->slot_vary.assign(t->slot_vary, t->slot_vary + (size_t)t->n_gen * DPS_N_SLOTS);
+    if (t->n_rec) pl->rec.assign(t->rec, t->rec + t->n_rec);
+    pl->topo.ctrl = pl->ctrl.data();
+    pl->topo.step_cfg = pl->step_cfg.data();
+    pl->topo.slot_vary = pl->slot_vary.data();
+    pl->topo.rec = pl->rec.data();
+
+    for (int k = 0; k < t->n_steps; ++k) {
+        if (pl->step_cfg[k] >= t->n_cfg) { set_error("dps_plan_create: step_cfg[%d]=%d >= n_cfg", k, pl->step_cfg[k]); delete pl; return 1; }
+        if (k == 0 || pl->step_cfg[k] != pl->step_cfg[k - 1]) { pl->seg_step.push_back(k); pl->seg_cfg.push_back(pl->step_cfg[k]); }
+    }
+    if (pl->seg_step.empty()) { pl->seg_step.push_back(0); pl->seg_cfg.push_back(0); }
+
+    pl->g_template = fwd_template_g(t->n_gen);
+    pl->any_ctrl = false;
+    pl->any_vary = false;
+    for (int g = 0; g < t->n_gen; ++g) pl->any_ctrl |= (pl->ctrl[g] != 0);
+    for (int v : pl->slot_vary) {
+        if (v >= t->n_vary) { set_error("dps_plan_create: slot_vary entry %d >= n_vary %d", v, t->n_vary); delete pl; return 1; }
+        pl->any_vary |= (v >= 0);
+    }
+
+    FwdParams& b = pl->base;
+    memset(&b, 0, sizeof(b));
+    b.n_gen = t->n_gen; b.solver = t->solver; b.n_steps = t->n_steps; b.dt = t->dt; b.fn = t->fn;
+    b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.z_per_sim = t->z_per_sim;
+    b.ckpt_stride = t->ckpt_stride;
+    for (int g = 0; g < t->n_gen; ++g) b.ctrl[g] = pl->ctrl[g];
+    for (size_t i = 0; i < pl->slot_vary.size(); ++i) b.slot_vary[i] = (short)pl->slot_vary[i];
+    for (int e = 0; e < MAX_EXTRA_OBS; ++e) b.obs_chan[e][0] = b.obs_chan[e][1] = -1;
+    for (int c = 0; c < t->n_rec; ++c) {
+        const dps_channel& ch = pl->rec[c];
+        if (ch.kind == DPS_CH_GEN) {
+            if (ch.index < 0 || ch.index >= t->n_gen || ch.field < 0 || ch.field >= DPS_N_FIELDS) {
+                set_error("dps_plan_create: recorder channel %d out of range", c); delete pl; return 1;
+            }
+            if (b.rec_mask[ch.index] & (1u << ch.field)) {
+                set_error("dps_plan_create: recorder channel %d duplicates generator %d field %d", c, ch.index, ch.field);
+                delete pl; return 1;
+            }
+            b.rec_mask[ch.index] |= (1u << ch.field);
+            b.rec_chan[ch.index][ch.field] = (short)c;
+        } else if (ch.kind == DPS_CH_BUS_VRE || ch.kind == DPS_CH_BUS_VIM) {
+            const int e = ch.index - t->n_gen;
+            if (e < 0 || ch.index >= t->n_obs) { set_error("dps_plan_create: bus channel %d must name an extra observed row", c); delete pl; return 1; }
+            short& slot = b.obs_chan[e][ch.kind == DPS_CH_BUS_VIM];
+            if (slot >= 0) { set_error("dps_plan_create: recorder channel %d duplicates an observed-bus channel", c); delete pl; return 1; }
+            slot = (short)c;
+        } else {
+            set_error("dps_plan_create: recorder channel %d has unknown kind %d", c, ch.kind); delete pl; return 1;
+        }
+    }
+    *out = pl;
+    return 0;
+}
+
+int dps_plan_destroy(dps_plan* plan) {
+    delete plan;
+    return 0;
+}
+
+int64_t dps_n_checkpoints(const dps_plan* plan) {
+    if (!plan || plan->topo.ckpt_stride <= 0) return 0;
+    return (plan->topo.n_steps + plan->topo.ckpt_stride - 1) / plan->topo.ckpt_stride;
+}
+
+int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_per_block, int32_t* regs_per_thread,
+                  int32_t* g_template) {
+    if (!plan) { set_error("dps_plan_info: null plan"); return 1; }
+    int th = 0, spb = 0;
+    fwd_geometry(plan->g_template, &th, &spb);
+    if (block_threads) *block_threads = th;
+    if (sims_per_block) *sims_per_block = spb;
+    if (g_template) *g_template = plan->g_template;
+    if (regs_per_thread) {
+        int regs = 0;
+        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->any_ctrl, plan->any_vary, 0, &regs);
+        if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
+        *regs_per_thread = regs;
+    }
+    return 0;
+}
+
+int dps_forward(const dps_plan* plan, int64_t P, const double* x0, const double* upar, const double* vpar,
+                const double* zsub, double* rec, double* x_final, double* ckpt, void* stream) {
+    if (!plan) { set_error("dps_forward: null plan"); return 1; }
+    if (P < 1) { set_error("dps_forward: P must be >= 1"); return 1; }
+    if (!x0 || !upar || !zsub) { set_error("dps_forward: null input pointer"); return 1; }
+    if (plan->topo.n_rec > 0 && !rec) { set_error("dps_forward: recorder channels requested but rec is null"); return 1; }
+    if (plan->any_vary && !vpar) { set_error("dps_forward: per-sim constants requested but vpar is null"); return 1; }
+    if (plan->topo.ckpt_stride > 0 && !ckpt) { set_error("dps_forward: checkpoints requested but ckpt is null"); return 1; }
+    if (plan->topo.n_steps == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // one launch per MAX_SEG configuration change points (virtually always a single launch)
+    const int n_seg = (int)plan->seg_step.size();
+    const double* x_in = x0;
+    int seg0 = 0;
+    while (seg0 < n_seg) {
+        const int seg1 = (seg0 + MAX_SEG < n_seg) ? seg0 + MAX_SEG : n_seg;
+        FwdParams p = plan->base;
+        p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub;
+        p.rec = rec; p.ckpt = ckpt;
+        p.step_begin = plan->seg_step[seg0];
+        p.step_end = (seg1 < n_seg) ? plan->seg_step[seg1] : plan->topo.n_steps;
+        p.n_seg = seg1 - seg0;
+        for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
+        const bool last = (seg1 == n_seg);
+        if (!last && !x_final) { set_error("dps_forward: more than %d configuration changes need x_final as carry buffer", MAX_SEG); return 1; }
+        p.x_final = x_final;
+        cudaError_t e = launch_forward(p, plan->g_template, plan->any_ctrl, plan->any_vary, st, nullptr);
+        if (e != cudaSuccess) { set_error("dps_forward: launch failed: %s", cudaGetErrorString(e)); return 3; }
+        x_in = x_final;
+        seg0 = seg1;
+    }
+    return 0;
+}
+
+int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const double* z_im, const double* yd_re,
+                       const double* yd_im, int32_t n_obs, const int32_t* obs_bus, int32_t n_gen, const int32_t* gen_bus,
+                       int32_t n_cfg, const int32_t* cfg_ptr, const int32_t* cfg_bus, double y_fault, double* zsub,
+                       void* stream) {
+    if (!z_re || !z_im || !yd_re || !yd_im || !obs_bus || !gen_bus || !cfg_ptr || !zsub) { set_error("dps_network_reduce: null argument"); return 1; }
+    if (Bz < 1 || n_bus < 1) { set_error("dps_network_reduce: bad sizes"); return 1; }
+    if (n_gen < 1 || n_gen > MAX_G || n_obs < n_gen || n_obs > MAX_G + MAX_EXTRA_OBS) { set_error("dps_network_reduce: n_gen/n_obs out of range"); return 1; }
+    if (n_cfg < 1 || n_cfg > RED_MAX_CFG) { set_error("dps_network_reduce: n_cfg %d out of range (max %d)", n_cfg, RED_MAX_CFG); return 1; }
+    ReduceParams p;
+    memset(&p, 0, sizeof(p));
+    p.Bz = Bz; p.n_bus = n_bus; p.n_obs = n_obs; p.n_gen = n_gen; p.n_cfg = n_cfg; p.y_fault = y_fault;
+    p.z_re = z_re; p.z_im = z_im; p.yd_re = yd_re; p.yd_im = yd_im; p.zsub = zsub;
+    for (int i = 0; i < n_obs; ++i) { if (obs_bus[i] < 0 || obs_bus[i] >= n_bus) { set_error("dps_network_reduce: obs_bus out of range"); return 1; } p.obs_bus[i] = obs_bus[i]; }
+    for (int i = 0; i < n_gen; ++i) { if (gen_bus[i] < 0 || gen_bus[i] >= n_bus) { set_error("dps_network_reduce: gen_bus out of range"); return 1; } p.gen_bus[i] = gen_bus[i]; }
+    int m_max = 0;
+    for (int c = 0; c < n_cfg; ++c) {
+        const int m = cfg_ptr[c + 1] - cfg_ptr[c];
+        if (m < 0 || m > RED_MAX_FAULT) { set_error("dps_network_reduce: configuration %d has %d faulted buses (max %d)", c, m, RED_MAX_FAULT); return 1; }
+        p.cfg_n[c] = m;
+        for (int k = 0; k < m; ++k) {
+            const int b = cfg_bus[cfg_ptr[c] + k];
+            if (b < 0 || b >= n_bus) { set_error("dps_network_reduce: faulted bus out of range"); return 1; }
+            p.cfg_bus[c][k] = b;
+        }
+        if (m > m_max) m_max = m;
+    }
+    p.m_max = m_max;
+    cudaError_t e = launch_network_reduce_params(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dps_network_reduce: launch failed: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds) {
+    if (!tflops || !milliseconds || iters < 1) { set_error("dps_fp64_peak_probe: bad argument"); return 1; }
+    cudaError_t e = run_fp64_probe(iters, tflops, milliseconds);
+    if (e != cudaSuccess) { set_error("dps_fp64_peak_probe: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- adjoint entry points: implemented in dps_backward.cu ------------------------------------------------

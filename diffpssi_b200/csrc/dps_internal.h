@@ -1,0 +1,60 @@
+// dps_internal.h -- structures shared between the ABI layer (dps_abi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dps.h"
+
+namespace dps {
+
+constexpr int MAX_G = 12;            // generators handled by the register-resident stepper
+constexpr int MAX_SEG = 48;          // network-configuration change points per launch
+constexpr int MAX_EXTRA_OBS = 24;    // recorded non-generator buses
+
+// Kernel parameter block (passed by value -> constant bank).
+struct FwdParams {
+    long long P;
+    int n_gen, solver, n_steps, step_begin, step_end;
+    double dt, fn;
+    const double* x0;        // [n_gen][13][P] state at step_begin
+    const double* upar;      // [n_gen][42]
+    const double* vpar;      // [n_vary][P]
+    const double* zsub;      // [n_cfg][z_rows][z_cols][2][Bz]
+    double* rec;             // [n_rec][n_steps][P]
+    double* x_final;         // [n_gen][13][P] or null
+    double* ckpt;            // [n_ckpt][n_gen][13][P] or null
+    int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_seg;
+    int seg_step[MAX_SEG];
+    int seg_cfg[MAX_SEG];
+    int ctrl[MAX_G];
+    unsigned rec_mask[MAX_G];               // bit k: field k of this generator is recorded
+    short rec_chan[MAX_G][DPS_N_FIELDS];    // channel index of field k
+    short obs_chan[MAX_EXTRA_OBS][2];       // channel of (re, im) of extra observed row e, or -1
+    short slot_vary[MAX_G * DPS_N_SLOTS];   // row of vpar or -1
+};
+
+int fwd_template_g(int n_gen);
+void fwd_geometry(int g_template, int* threads, int* sims_per_block);
+cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, bool vary, cudaStream_t stream,
+                           int* regs_query);
+
+constexpr int RED_MAX_CFG = 16;      // distinct faulted-bus sets per run
+constexpr int RED_MAX_FAULT = 8;     // simultaneously faulted buses
+
+struct ReduceParams {
+    long long Bz;
+    int n_bus, n_obs, n_gen, n_cfg, m_max;
+    double y_fault;
+    const double *z_re, *z_im, *yd_re, *yd_im;
+    double* zsub;
+    int obs_bus[MAX_G + MAX_EXTRA_OBS];
+    int gen_bus[MAX_G];
+    int cfg_n[RED_MAX_CFG];
+    int cfg_bus[RED_MAX_CFG][RED_MAX_FAULT];
+};
+cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream);
+
+cudaError_t run_fp64_probe(int iters, double* tflops, double* ms);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace dps

@@ -1,0 +1,142 @@
+// dps_model.cuh -- the per-generator stage evaluation shared by the forward stepper and the adjoint.
+//
+// Real-fp64 restatement of what one stage of solver.step() does for one generator of one trajectory
+// (reference file:line in the comments below).  The reference carries complex128 tensors whose imaginary
+// part is identically zero for every *state* (SURVEY.md fact 3); only bus voltages / currents / Z are complex,
+// and those are handled here as explicit (re, im) pairs.
+#pragma once
+#include <math.h>
+#include "../../include/dps.h"
+
+namespace dps {
+
+// Reads constant `slot` of the generator this thread works on.  UP = uniform table in shared memory,
+// VARY=true adds the per-sim override path.
+template <bool VARY>
+struct ParamReader {
+    const double* up;        // shared memory, [DPS_N_SLOTS] of this generator
+    const short*  sv;        // shared memory, [DPS_N_SLOTS] row in vpar or -1
+    const double* vpar;      // global [n_vary][P]
+    long long     P, s;
+    __device__ __forceinline__ double operator()(int slot) const {
+        if (VARY) {
+            const int vi = sv[slot];
+            if (vi >= 0) return __ldg(vpar + (long long)vi * P + s);
+        }
+        return up[slot];
+    }
+};
+
+struct Algebraics {            // values the reference keeps on the machine object after a stage
+    double p_e, i_d, i_q, v_re, v_im, e_fd, p_m;
+};
+
+// Norton current injection, synchronous_machine.py:256-260:
+//   i_d = e_q''/(j x_d'') e^{j delta},  i_q = e_d''/(j x_q'') e^{j(delta - pi/2)},  I = (i_d + i_q) S_n/S_sys
+// with e^{j delta} = c + j s and e^{j(delta-pi/2)} = s - j c this is
+//   I = snr * [ (a s - b c) - j (a c + b s) ],  a = e_q''/x_d'',  b = e_d''/x_q''
+template <class PR>
+__device__ __forceinline__ void injection(const double* x, const PR& par, double sd, double cd,
+                                          double& i_re, double& i_im) {
+    const double a = x[DPS_X_EQST] * par(DPS_S_INV_XDST);
+    const double b = x[DPS_X_EDST] * par(DPS_S_INV_XQST);
+    const double snr = par(DPS_S_SNR);
+    i_re = (a * sd - b * cd) * snr;
+    i_im = (-(a * cd) - b * sd) * snr;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) {
+    return fmin(fmax(v, lo), hi);      // blocks.py:181, 241: minimum(maximum(x.real, lo), hi)
+}
+
+// Anti-windup gate of PT1Limited.differential, blocks.py:145-149: `<=`/`>=` on the state, strict on the derivative
+__device__ __forceinline__ double windup_gate(double state, double dx, double lo, double hi) {
+    const bool stop = ((state <= lo) && (dx < 0.0)) || ((state >= hi) && (dx > 0.0));
+    return stop ? 0.0 : dx;
+}
+
+// One stage for one generator, given its bus voltage (v_re, v_im): update_internal_vars
+// (synchronous_machine.py:271-277) + differential() (synchronous_machine.py:148-172) with the controller
+// get_output()/differential() pairs it calls.  Writes f[0..12] (zero for absent controllers).
+template <bool CTRL, class PR>
+__device__ __forceinline__ void stage_derivatives(const double* x, const PR& par, int ctrl, double fn,
+                                                  double sd, double cd, double v_re, double v_im,
+                                                  double* f, Algebraics& alg) {
+    const double omega = x[DPS_X_OMEGA];
+    const double eqst = x[DPS_X_EQST], edst = x[DPS_X_EDST];
+    // e'' = e_q'' e^{j delta} + e_d'' e^{j(delta - pi/2)}                              :273
+    const double e_re = eqst * cd + edst * sd;
+    const double e_im = eqst * sd - edst * cd;
+    // i_gen = (e'' - v)/(j x_d'')   (x_d'' on both axes, as the reference)             :275
+    const double inv_xdst = par(DPS_S_INV_XDST);
+    const double i_re = (e_im - v_im) * inv_xdst;
+    const double i_im = -((e_re - v_re) * inv_xdst);
+    const double p_e = v_re * i_re + v_im * i_im;                                    // :274
+    // (i_d + j i_q) = i_gen e^{j(pi/2 - delta)} = i_gen (s + j c)                      :276-277
+    const double i_d = i_re * sd - i_im * cd;
+    const double i_q = i_re * cd + i_im * sd;
+
+    double e_fd = par(DPS_S_EFD0);      // held constant without an exciter (synchronous_machine.py:314)
+    double p_m = par(DPS_S_PM0);        // held constant without a governor (synchronous_machine.py:313)
+#pragma unroll
+    for (int k = 6; k < DPS_N_STATES; ++k) f[k] = 0.0;
+
+    if (CTRL) {
+        double v_pss = 0.0;
+        if (ctrl & DPS_CTRL_PSS) {
+            // STAB1.get_output is only called when an exciter exists (synchronous_machine.py:148-150); without
+            // one the block inputs keep their initial 0 and only the decay terms remain.
+            const bool fed = (ctrl & DPS_CTRL_AVR) != 0;
+            const double xw = x[DPS_X_PSS_W], x1 = x[DPS_X_PSS_LL1], x2 = x[DPS_X_PSS_LL2];
+            // Washout: output == derivative, blocks.py:382, 413
+            const double w = par(DPS_S_S_INV_TW) * (par(DPS_S_S_KW) * (fed ? omega : 0.0) - xw);
+            const double in1 = fed ? w : 0.0;
+            const double o1 = par(DPS_S_S_R1) * in1 + par(DPS_S_S_OMR1) * x1;        // blocks.py:319
+            const double in2 = fed ? o1 : 0.0;
+            const double o2 = par(DPS_S_S_R2) * in2 + par(DPS_S_S_OMR2) * x2;
+            f[DPS_X_PSS_W] = w;
+            f[DPS_X_PSS_LL1] = par(DPS_S_S_INV_T3) * (in1 - x1);                     // blocks.py:290
+            f[DPS_X_PSS_LL2] = par(DPS_S_S_INV_T4) * (in2 - x2);
+            const double hl = par(DPS_S_S_HLIM);
+            v_pss = clampd(o2, -hl, hl);                                             // blocks.py:241
+        }
+        if (ctrl & DPS_CTRL_AVR) {
+            // SEXS.get_output(|v_bb| - v_pss), exciters.py:111-114
+            const double v_abs = sqrt(v_re * v_re + v_im * v_im);
+            const double sig = (ctrl & DPS_CTRL_PSS) ? (v_abs - v_pss) : v_abs;
+            const double u = (par(DPS_S_A_VSET) - sig) + par(DPS_S_A_BIAS);
+            const double xll = x[DPS_X_AVR_LL], xe = x[DPS_X_AVR_PT1];
+            const double o = par(DPS_S_A_R) * u + par(DPS_S_A_OMR) * xll;
+            const double emin = par(DPS_S_A_EMIN), emax = par(DPS_S_A_EMAX);
+            e_fd = clampd(xe, emin, emax);
+            f[DPS_X_AVR_LL] = par(DPS_S_A_INV_TB) * (u - xll);
+            const double dxe = par(DPS_S_A_INV_TE) * (par(DPS_S_A_K) * o - xe);      // blocks.py:143
+            f[DPS_X_AVR_PT1] = windup_gate(xe, dxe, emin, emax);
+        }
+        if (ctrl & DPS_CTRL_GOV) {
+            // TGOV1.get_output(omega), governors.py:115-123
+            const double u = par(DPS_S_G_PREF) - omega;
+            const double xg = x[DPS_X_GOV_PT1], xll = x[DPS_X_GOV_LL];
+            const double vmin = par(DPS_S_G_VMIN), vmax = par(DPS_S_G_VMAX);
+            const double gs = clampd(xg, vmin, vmax);
+            const double o = par(DPS_S_G_R) * gs + par(DPS_S_G_OMR) * xll;
+            p_m = o - par(DPS_S_G_DT) * omega;
+            const double dxg = par(DPS_S_G_INV_T1) * (par(DPS_S_G_GAIN) * u - xg);
+            f[DPS_X_GOV_PT1] = windup_gate(xg, dxg, vmin, vmax);
+            f[DPS_X_GOV_LL] = par(DPS_S_G_INV_T3) * (gs - xll);
+        }
+    }
+
+    // synchronous_machine.py:158-164
+    const double t_m = p_m / (1.0 + omega);
+    f[DPS_X_OMEGA] = par(DPS_S_INV_2H) * ((t_m - p_e) - par(DPS_S_D) * omega);
+    f[DPS_X_DELTA] = ((omega * 2.0) * 3.141592653589793) * fn;
+    f[DPS_X_EQT] = par(DPS_S_INV_TD0T) * ((e_fd - x[DPS_X_EQT]) - i_d * par(DPS_S_XD_XDT));
+    f[DPS_X_EDT] = par(DPS_S_INV_TQ0T) * (-x[DPS_X_EDT] + i_q * par(DPS_S_XQ_XQT));
+    f[DPS_X_EQST] = par(DPS_S_INV_TD0ST) * ((x[DPS_X_EQT] - eqst) - i_d * par(DPS_S_XDT_XDST));
+    f[DPS_X_EDST] = par(DPS_S_INV_TQ0ST) * ((x[DPS_X_EDT] - edst) + i_q * par(DPS_S_XQT_XQST));
+
+    alg.p_e = p_e; alg.i_d = i_d; alg.i_q = i_q; alg.v_re = v_re; alg.v_im = v_im; alg.e_fd = e_fd; alg.p_m = p_m;
+}
+
+}  // namespace dps

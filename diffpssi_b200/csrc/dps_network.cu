@@ -1,0 +1,132 @@
+// dps_network.cu -- on-device fault re-reduction of the bus impedance matrix, and the fp64 peak probe.
+//
+// Reference behaviour being replaced (src/diffpssi/power_sim_lib/simulator.py:524-531): on EVERY step in which a
+// short circuit is active the reference does two dense batched inversions,
+//     Y = inv(Z);  Y[:, b, b] = 1e6;  Z = inv(Y)
+// and restores Z = Z_original when it is not.  Setting one diagonal entry of Y is a rank-1 change
+// dY = c e_b e_b^T with c = 1e6 - Y_bb, so by Sherman-Morrison
+//     Z' = Z - f Z[:,b] Z[b,:],    f = c / (1 + c Z_bb)
+// and the stepper only ever needs rows {observed buses} x columns {generator buses} of Z'.  One thread per
+// trajectory (or a single thread when the network is shared by the batch) applies the updates for every
+// distinct set of simultaneously faulted buses ("configuration") once, before the time loop.
+#include <cuda_runtime.h>
+#include "dps_internal.h"
+
+namespace dps {
+
+__global__ void dps_network_reduce_kernel(const ReduceParams p) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.Bz) return;
+    const long long B = p.Bz;
+    const int rows = p.n_obs + p.m_max, cols = p.n_gen + p.m_max;
+    for (int cfg = 0; cfg < p.n_cfg; ++cfg) {
+        double* W = p.zsub + (long long)cfg * rows * cols * 2 * B + b;
+        const int m = p.cfg_n[cfg];
+        auto w_re = [&](int r, int c) -> double& { return W[((long long)(r * cols + c) * 2) * B]; };
+        auto w_im = [&](int r, int c) -> double& { return W[((long long)(r * cols + c) * 2 + 1) * B]; };
+        // gather rows {observed, faulted} x columns {generators, faulted}
+        for (int r = 0; r < rows; ++r) {
+            const int rb = (r < p.n_obs) ? p.obs_bus[r] : ((r - p.n_obs) < m ? p.cfg_bus[cfg][r - p.n_obs] : -1);
+            for (int c = 0; c < cols; ++c) {
+                const int cbus = (c < p.n_gen) ? p.gen_bus[c] : ((c - p.n_gen) < m ? p.cfg_bus[cfg][c - p.n_gen] : -1);
+                double re = 0.0, im = 0.0;
+                if (rb >= 0 && cbus >= 0) {
+                    const long long o = ((long long)rb * p.n_bus + cbus) * B + b;
+                    re = p.z_re[o];
+                    im = p.z_im[o];
+                }
+                w_re(r, c) = re;
+                w_im(r, c) = im;
+            }
+        }
+        // one Sherman-Morrison update per faulted bus (the diagonal of Y is SET to y_fault: simulator.py:527)
+        for (int k = 0; k < m; ++k) {
+            const int fb = p.cfg_bus[cfg][k];
+            const int rk = p.n_obs + k, ck = p.n_gen + k;
+            const double c_re = p.y_fault - p.yd_re[(long long)fb * B + b];
+            const double c_im = -p.yd_im[(long long)fb * B + b];
+            const double zbb_re = w_re(rk, ck), zbb_im = w_im(rk, ck);
+            // den = 1 + c * Z_bb ; f = c / den
+            const double den_re = 1.0 + (c_re * zbb_re - c_im * zbb_im);
+            const double den_im = c_re * zbb_im + c_im * zbb_re;
+            const double dn = den_re * den_re + den_im * den_im;
+            const double f_re = (c_re * den_re + c_im * den_im) / dn;
+            const double f_im = (c_im * den_re - c_re * den_im) / dn;
+            // rows other than the faulted one first (they need the OLD faulted row), then the faulted row itself
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int r = 0; r < rows; ++r) {
+                    if ((r == rk) != (pass == 1)) continue;
+                    const double a_re = w_re(r, ck), a_im = w_im(r, ck);           // Z[r][b] (old)
+                    const double t_re = f_re * a_re - f_im * a_im;
+                    const double t_im = f_re * a_im + f_im * a_re;                  // f * Z[r][b]
+                    for (int c = 0; c < cols; ++c) {
+                        const double b_re = w_re(rk, c), b_im = w_im(rk, c);       // Z[b][c] (old: for r==rk it is this entry)
+                        w_re(r, c) -= t_re * b_re - t_im * b_im;
+                        w_im(r, c) -= t_re * b_im + t_im * b_re;
+                    }
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream) {
+    const int threads = 128;
+    const long long blocks = (p.Bz + threads - 1) / threads;
+    dps_network_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp64 peak probe: 8 independent DFMA chains per thread, enough warps to fill every SM
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dps_fp64_probe_kernel(double* out, int iters, double a, double b) {
+    double r0 = threadIdx.x * 1e-3, r1 = r0 + 1.0, r2 = r0 + 2.0, r3 = r0 + 3.0;
+    double r4 = r0 + 4.0, r5 = r0 + 5.0, r6 = r0 + 6.0, r7 = r0 + 7.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 12345.678) out[0] = s;      // never true: keeps the chains alive
+}
+
+cudaError_t run_fp64_probe(int iters, double* tflops, double* ms_out) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    double* d_out = nullptr;
+    e = cudaMalloc(&d_out, sizeof(double));      // probe only (measurement helper, not the data path)
+    if (e != cudaSuccess) return e;
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    dps_fp64_probe_kernel<<<blocks, threads>>>(d_out, iters / 8 + 1, 0.999999, 1e-9);     // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0);
+        dps_fp64_probe_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return e;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    *ms_out = best;
+    return cudaGetLastError();
+}
+
+}  // namespace dps

@@ -1,0 +1,135 @@
+"""Host-side planning: turn (grid, initial state, events, recorder channels) into the flat buffers and the
+``dps_topology`` the C ABI takes (include/dps.h).  Pure host logic -- testable without a GPU.
+"""
+import numpy as np
+import torch
+
+from . import engine
+from .prologue import SLOTS, SLOT_INDEX, N_SLOTS, CTRL_AVR, CTRL_GOV, CTRL_PSS
+
+F64 = torch.float64
+FIELD_VRE, FIELD_VIM = 16, 17
+FAULT_ADMITTANCE = 1e6          # simulator.py:527
+
+
+def event_schedule(time_grid, sc_events):
+    """Per-step network configuration, reproducing simulator.py:524-531 *including* its multi-event quirk:
+
+        for ev in sc_events:                      # list order
+            if ev.is_active(t):  Z <- fault(Z_current, ev.bus)      (Y=inv(Z); Y[b,b]=1e6; Z=inv(Y))
+            else:                Z <- Z_original
+
+    Faulting is idempotent and order-independent (it *sets* diagonal entries of Y), so the matrix in force during a
+    step is determined by a *set* of faulted buses: an inactive event wipes the set (also faults applied by earlier
+    events in the list, and faults carried over from the previous step), an active one adds its bus.
+    Returns (step_cfg uint8[T], cfg_sets) with cfg_sets[0] == () always.
+    """
+    cfg_sets = [()]
+    step_cfg = np.zeros(len(time_grid), dtype=np.uint8)
+    cur = frozenset()
+    for k, t in enumerate(time_grid):
+        for ev in sc_events:
+            cur = (cur | {int(ev.bus)}) if ev.is_active(t) else frozenset()
+        key = tuple(sorted(cur))
+        if key not in cfg_sets:
+            cfg_sets.append(key)
+        step_cfg[k] = cfg_sets.index(key)
+    if len(cfg_sets) > engine.MAX_CFG:
+        raise engine.EngineError('too many distinct fault configurations (%d > %d)' % (len(cfg_sets), engine.MAX_CFG))
+    if max(len(s) for s in cfg_sets) > engine.MAX_FAULT:
+        raise engine.EngineError('too many simultaneously faulted buses')
+    return step_cfg, cfg_sets
+
+
+def canonical_x0(init, P):
+    """[G,13,P] initial states in the kernel's canonical layout (absent controllers -> zero rows)."""
+    rows = []
+    for x0, flags in zip(init.x0, init.ctrl):
+        it = iter(x0)
+        mach = [next(it) for _ in range(6)]
+        avr = [next(it), next(it)] if flags & CTRL_AVR else [None, None]
+        gov = [next(it), next(it)] if flags & CTRL_GOV else [None, None]
+        pss = [next(it), next(it), next(it)] if flags & CTRL_PSS else [None, None, None]
+        dev = mach[1].device
+        zero = torch.zeros(P, dtype=F64, device=dev)
+        cols = [zero if v is None else v.reshape(-1).to(F64).expand(P) for v in mach + avr + gov + pss]
+        rows.append(torch.stack(cols, dim=0))
+    return torch.stack(rows, dim=0).contiguous()
+
+
+def pack_slots(init, P, device):
+    """upar [G,42] (uniform constants), vpar [n_vary,P] (per-sim constants), slot_vary list[G*42]."""
+    G = len(init.slots)
+    zero1 = torch.zeros(1, dtype=F64, device=device)
+    urows, vrows, slot_vary = [], [], []
+    for sl in init.slots:
+        ucols = []
+        for name in SLOTS:
+            v = sl.get(name)
+            if v is None:
+                ucols.append(zero1)
+                slot_vary.append(-1)
+                continue
+            v = v.reshape(-1).to(F64)
+            if v.shape[0] == 1:
+                ucols.append(v)
+                slot_vary.append(-1)
+            else:
+                ucols.append(zero1)
+                slot_vary.append(len(vrows))
+                vrows.append(v)
+        urows.append(torch.cat(ucols))
+    upar = torch.stack(urows, dim=0).contiguous()
+    vpar = torch.stack(vrows, dim=0).contiguous() if vrows else None
+    return upar, vpar, slot_vary
+
+
+def observed_rows(init, channel_keys):
+    """Rows of the reduced impedance matrix: the generator buses (generator order) then every recorded bus that hosts
+    no generator.  Also rewrites recorder keys into C-ABI channels."""
+    gen_bus = list(init.gen_bus)
+    first_gen_on_bus = {}
+    for gi, b in enumerate(gen_bus):
+        first_gen_on_bus.setdefault(b, gi)
+    obs_bus = list(gen_bus)
+    chans = []
+    for key in channel_keys:
+        if key[0] == 'gen':
+            chans.append((engine.CH_GEN, key[1], key[2]))
+        else:
+            _, bus, part = key
+            if bus in first_gen_on_bus:
+                chans.append((engine.CH_GEN, first_gen_on_bus[bus], FIELD_VIM if part else FIELD_VRE))
+            else:
+                if bus not in obs_bus[len(gen_bus):]:
+                    obs_bus.append(bus)
+                row = len(gen_bus) + obs_bus[len(gen_bus):].index(bus)
+                chans.append((engine.CH_BUS_VIM if part else engine.CH_BUS_VRE, row, 0))
+    if len(obs_bus) - len(gen_bus) > engine.MAX_EXTRA_OBS:
+        raise engine.EngineError('too many recorded non-generator buses')
+    return obs_bus, chans
+
+
+def split_complex_batch_last(z):
+    """complex [B, ...] -> (re, im) float64 [..., B] contiguous (batch innermost, the kernels' layout)."""
+    perm = list(range(1, z.dim())) + [0]
+    return z.real.permute(perm).contiguous(), z.imag.permute(perm).contiguous()
+
+
+def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
+    """-> (topo dict for engine.Plan, dict of host-side extras)."""
+    step_cfg, cfg_sets = event_schedule(sim.time, sim.sc_events)
+    obs_bus, chans = observed_rows(init, channel_keys)
+    G = len(init.gens)
+    if G > engine.MAX_G:
+        raise engine.EngineError('%d generators: the register-resident stepper handles up to %d' % (G, engine.MAX_G))
+    m_max = max(len(s) for s in cfg_sets)
+    topo = {
+        'n_gen': G, 'solver': engine.SOLVER_ID[solver_name], 'n_steps': len(sim.time), 'dt': float(sim.time_step),
+        'fn': float(sim.fn), 'ctrl': list(init.ctrl), 'n_obs': len(obs_bus),
+        'z_rows': len(obs_bus) + m_max, 'z_cols': G + m_max, 'n_cfg': len(cfg_sets),
+        'step_cfg': step_cfg.tolist(), 'z_per_sim': int(init.Z0.shape[0] > 1), 'rec': chans,
+        'ckpt_stride': int(ckpt_stride),
+    }
+    extras = {'cfg_sets': cfg_sets, 'obs_bus': obs_bus, 'gen_bus': list(init.gen_bus), 'm_max': m_max}
+    return topo, extras

@@ -198,7 +198,6 @@ def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
     G, Bm = y_bus.real, y_bus.imag
     ia = torch.tensor(ang_ids, device=dev, dtype=torch.long)
     iq = torch.tensor(pq, device=dev, dtype=torch.long)
-    eye_a = torch.eye(n_ang, dtype=torch.bool, device=dev)
     it = 0
     while True:
         s_calc = V * torch.conj(torch.matmul(y_bus, V.unsqueeze(-1)).squeeze(-1))
@@ -241,7 +240,6 @@ def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
         if it > max_iter:
             raise ValueError('Load flow did not converge')
         it += 1
-    del eye_a
     s_calc = V * torch.conj(torch.matmul(y_bus, V.unsqueeze(-1)).squeeze(-1))
     return V, s_calc, it
 
@@ -251,8 +249,7 @@ def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
 # ==================================================================================================
 class InitResult(object):
     """What the time loop consumes."""
-    __slots__ = ('gens', 'gen_bus', 'ctrl', 'x0', 'slots', 'Z0', 'Ydiag', 'bus_v', 's_calc', 'lf_iters',
-                 'omega_scale')
+    __slots__ = ('gens', 'gen_bus', 'ctrl', 'x0', 'slots', 'xst', 'Z0', 'Ydiag', 'bus_v', 's_calc', 'lf_iters')
 
 
 def _clamp(x, lo, hi):
@@ -273,8 +270,7 @@ def initialize(sim, device):
     gens = generators_of(sim)
     res.gens = [g for _, g in gens]
     res.gen_bus = [bi for bi, _ in gens]
-    res.ctrl, res.x0, res.slots = [], [], []
-    res.omega_scale = None
+    res.ctrl, res.x0, res.slots, res.xst = [], [], [], []
 
     # loads become constant admittances from the load-flow voltage (static_models.py:515-527)
     for bi, bus in enumerate(sim.busses):
@@ -365,6 +361,7 @@ def initialize(sim, device):
                        's_inv_t3': _real(1 / t3), 's_r2': _real(r2), 's_omr2': _real(1 - r2),
                        's_inv_t4': _real(1 / t4), 's_hlim': _real(col(st.limiter.limit, None))})
         res.ctrl.append(flags)
+        res.xst.append((c['x_d_st'], c['x_q_st']))
         res.x0.append(x0)
         res.slots.append(sl)
         # expose initial values on the container, as the reference does
@@ -379,13 +376,13 @@ def initialize(sim, device):
     return res
 
 
-def initial_injections(res, device):
+def initial_injections(res):
     """Norton current injections of every generator at x0 (synchronous_machine.py:256-260), [B,G] complex."""
     cur = []
-    for x0, sl in zip(res.x0, res.slots):
+    for x0, sl, (xdst, xqst) in zip(res.x0, res.slots, res.xst):
         delta, eq, ed = x0[1], x0[4], x0[5]
-        i_d = eq / (1j / sl['inv_xdst']) * torch.exp(1j * delta)
-        i_q = ed / (1j / sl['inv_xqst']) * torch.exp(1j * (delta - math.pi / 2))
+        i_d = eq / (1j * xdst) * torch.exp(1j * delta)
+        i_q = ed / (1j * xqst) * torch.exp(1j * (delta - math.pi / 2))
         cur.append((i_d + i_q) * sl['snr'])
     B = max(c.shape[0] for c in cur)
     return torch.cat([c.expand(B, 1) for c in cur], dim=1)

@@ -1,0 +1,285 @@
+"""``PowerSystemSimulation`` -- the reference's ``Pss`` API with ``backend='cuda'``.
+
+Drop-in mirror of src/diffpssi/power_sim_lib/simulator.py:21-552 for the path this package accelerates:
+
+    Pss(time_step, sim_time, parallel_sims, solver, grid_data=None, verbose=True, backend='cuda')
+    add_bus / add_generator / add_load / add_shunt / add_line / add_transformer / add_exciter / add_governor /
+    add_pss, set_slack_bus, add_sc_event, add_param_event, set_record_function, reset, initialize, run
+
+``run()`` returns ``(time, result)`` with ``result[batch, timestep, value]`` exactly like simulator.py:546.
+Everything before the time loop is host torch code (``prologue.py``); the loop itself is ONE call into the CUDA
+engine (``engine.py`` -> ``libdps_b200.so``).  There is no numpy/torch stepping path in this package: the
+reference's own backends are what ``backend='numpy'|'torch'`` mean, and asking for them here raises.
+"""
+import os
+import time as _time
+
+import numpy as np
+import torch
+
+from . import engine, planning, prologue, recording
+from .autograd import StepFunction
+from .components import (Bus, Line, Transformer, Load, Shunt, SynchMachine, SEXS, TGOV1, STAB1, ScEvent,
+                         ParamEvent)
+
+SOLVERS = ('euler', 'heun', 'rk4')            # solvers.py:226-230
+BACKEND = os.environ.get('DIFFPSSI_FORCE_SIM_BACKEND', 'cuda')      # backend.py:11-14
+
+
+def _tabular(value):
+    """List-of-lists table (first row = keys) -> list of dicts (simulator.py:139-154)."""
+    keys = value[0]
+    return [dict(zip(keys, row)) for row in value[1:]]
+
+
+class PowerSystemSimulation(object):
+
+    def __init__(self, time_step, sim_time, parallel_sims, solver, grid_data=None, verbose=True,
+                 backend=None, device=None, ckpt_stride=32):
+        backend = backend or BACKEND
+        if backend != 'cuda':
+            raise ValueError("diffpssi_b200 implements backend='cuda' only (got %r); the numpy/torch backends are "
+                             "the reference's own" % (backend,))
+        self.backend = backend
+        if device is None:
+            device = 'cuda' if torch.cuda.is_available() else 'cpu'      # cpu: host-side logic only (tests)
+        self.device = str(device)
+        self.time = np.arange(0, sim_time, time_step)                       # simulator.py:78
+        self.time_step = time_step
+        self.busses, self.non_slack_busses, self.bus_idxs = [], [], {}
+        self.lines, self.trafos = [], []
+        self.inverse_dynamic_y_matrix = None
+        self.static_y_matrix = None
+        self.sc_events, self.param_events = [], []
+        self.parallel_sims = parallel_sims
+        self.record_func = None
+        self.record_channels = None
+        self.verbose = verbose
+        self.ckpt_stride = ckpt_stride
+        forced = os.environ.get('DIFFPSSI_FORCE_INTEGRATOR')                # simulator.py:96-100
+        if forced is not None:
+            print('WARNING: FORCING THE USE OF THE {} INTEGRATOR. '
+                  'THIS SHOULD ONLY HAPPEN FOR UNITTESTS'.format(forced))
+            solver = forced
+        if solver not in SOLVERS:
+            raise KeyError(solver)
+        self.solver = solver
+        self.base_voltage = self.base_mva = self.fn = None
+        self.last_init = None
+        self.last_plan = None
+        self.timings = {}
+        if grid_data is not None:
+            self.create_grid(grid_data)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # grid construction (simulator.py:113-348)
+    # ------------------------------------------------------------------------------------------------------------
+    def get_generator_by_name(self, name):
+        for bus in self.busses:
+            for model in bus.models:
+                if getattr(model, 'name', None) == name:
+                    return model
+        return None
+
+    def create_grid(self, grid_data):
+        self.fn = grid_data['f']
+        self.base_mva = grid_data['base_mva']
+        self.base_voltage = grid_data['base_voltage']
+        data = {}
+        for key, value in grid_data.items():
+            if isinstance(value, list) and all(isinstance(item, list) for item in value):
+                data[key] = _tabular(value)
+            elif isinstance(value, dict):
+                data[key] = {sub: _tabular(tab) for sub, tab in value.items()}
+            else:
+                data[key] = value
+        for d in data['busses']:
+            self.add_bus(Bus(param_dict=d))
+        gens = data.get('generators', [])
+        if isinstance(gens, dict):
+            for d in gens['GEN']:
+                self.add_generator(SynchMachine(param_dict=d, s_n_sys=self.base_mva, v_n_sys=self.base_voltage,
+                                                f_n_sys=self.fn))
+        for d in data.get('loads', []):
+            self.add_load(Load(param_dict=d, s_n_sys=self.base_mva))
+        for d in data.get('shunts', []):
+            self.add_shunt(Shunt(param_dict=d, s_n_sys=self.base_mva))
+        for d in data.get('lines', []):
+            self.add_line(Line(param_dict=d, s_n_sys=self.base_mva, v_n_sys=self.base_voltage))
+        for d in data.get('transformers', []):
+            self.add_transformer(Transformer(param_dict=d, s_n_sys=self.base_mva))
+        for key, sub, cls, adder in (('avr', 'SEXS', SEXS, self.add_exciter), ('gov', 'TGOV1', TGOV1, self.add_governor),
+                                     ('pss', 'STAB1', STAB1, self.add_pss)):
+            table = data.get(key, [])
+            if isinstance(table, dict):
+                for d in table[sub]:
+                    adder(cls(param_dict=d))
+        self.set_slack_bus(data['slack_bus'])
+
+    def set_slack_bus(self, slack_bus):
+        self.busses[self.bus_idxs[slack_bus]].lf_type = 'SL'
+
+    def _par(self, model):
+        model.enable_parallel_simulation(self.parallel_sims, self.device)
+        return model
+
+    def add_bus(self, bus_model):
+        self.bus_idxs[bus_model.name] = len(self.busses)
+        self.busses.append(self._par(bus_model))
+
+    def _bus_of(self, model):
+        return self.busses[self.bus_idxs[model.bus]]
+
+    def add_generator(self, generator_model):
+        bus = self._bus_of(generator_model)
+        bus.add_model(self._par(generator_model))
+        bus.voltage = generator_model.v_soll          # simulator.py:244
+        bus.lf_type = 'PV'
+
+    def add_load(self, load_model):
+        self._bus_of(load_model).add_model(self._par(load_model))
+
+    def add_shunt(self, shunt_model):
+        self._bus_of(shunt_model).add_model(self._par(shunt_model))
+
+    def _add_branch(self, model, store):
+        model.from_bus_id = self.bus_idxs[model.from_bus_name]
+        model.to_bus_id = self.bus_idxs[model.to_bus_name]
+        store.append(self._par(model))
+
+    def add_line(self, line_model):
+        self._add_branch(line_model, self.lines)
+
+    def add_transformer(self, transformer_model):
+        self._add_branch(transformer_model, self.trafos)
+
+    def add_exciter(self, exciter_model):
+        generator = self.get_generator_by_name(exciter_model.gen)
+        exciter_model.v_setpoint = generator.v_soll   # simulator.py:319
+        generator.add_exciter(self._par(exciter_model))
+
+    def add_governor(self, governor_model):
+        self.get_generator_by_name(governor_model.gen).add_governor(self._par(governor_model))
+
+    def add_pss(self, pss_model):
+        self.get_generator_by_name(pss_model.gen).add_pss(self._par(pss_model))
+
+    def add_inverter(self, inverter_model):
+        raise NotImplementedError('inverter models are outside the accelerated path (unused by the reference examples)')
+
+    def add_sc_event(self, start_time, end_time, bus):
+        self.sc_events.append(ScEvent(start_time, end_time, self.bus_idxs[bus]))
+
+    def add_param_event(self, timestep, model, parameter, new_val):
+        self.param_events.append(ParamEvent(timestep, model, parameter, new_val))
+
+    def set_record_function(self, record_func):
+        self.record_func = record_func
+        self.record_channels = None
+
+    def set_record_channels(self, names):
+        """Extension: recorder channels by name ('G1.omega', 'bus:B8.v_re', ...) instead of a Python callable."""
+        self.record_channels = list(names)
+        self.record_func = None
+
+    def reset(self):
+        """simulator.py:485-495 / static_models.py:189-197: bus voltages back to the last model's set point (or 1.0),
+        cached matrices dropped.  The next run() redoes load flow and initialisation from scratch."""
+        P = self.parallel_sims
+        for bus in self.busses:
+            v = getattr(bus.models[-1], 'v_soll', None) if bus.models else None
+            bus.voltage = v if v is not None else torch.ones((P, 1), dtype=torch.complex128, device=self.device)
+        for ev in self.param_events:
+            ev.handled = False
+        self.static_y_matrix = None
+        self.inverse_dynamic_y_matrix = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    # prologue + time loop
+    # ------------------------------------------------------------------------------------------------------------
+    def initialize(self):
+        """Load flow, model initialisation, Z = inv(Y_dyn), initial bus voltages (simulator.py:438-450)."""
+        init = prologue.initialize(self, self.device)
+        self.inverse_dynamic_y_matrix = init.Z0
+        P = self.parallel_sims
+        cur = prologue.initial_injections(init)                                   # [B,G]
+        B = max(cur.shape[0], init.Z0.shape[0])
+        n = len(self.busses)
+        inj = torch.zeros((B, n), dtype=torch.complex128, device=self.device)
+        cols = [inj[:, i] for i in range(n)]
+        for gi, b in enumerate(init.gen_bus):
+            cols[b] = cols[b] + cur[:, gi]
+        inj = torch.stack(cols, dim=1)
+        volt = torch.matmul(init.Z0, inj.unsqueeze(-1)).squeeze(-1)               # simulator.py:447
+        for i, bus in enumerate(self.busses):
+            bus.voltage = volt[:, i:i + 1].expand(P, 1)
+        self.last_init = init
+        return init
+
+    def _trace_recorder(self, init):
+        if self.record_channels is not None:
+            return recording.from_names(self, init.gens, self.record_channels)
+        if self.record_func is None:
+            raise TypeError('No record function specified')
+        return recording.trace(self, init.gens, self.record_func)
+
+    def run(self):
+        """Initialise, integrate every step of every trajectory on the GPU, return (time, result[P,T,n])."""
+        if self.param_events:
+            raise NotImplementedError('ParamEvent scheduling is not part of this round (SURVEY.md section 8f.3)')
+        t0 = _time.time()
+        init = self.initialize()
+        P, dev = self.parallel_sims, self.device
+        rplan = self._trace_recorder(init)
+        engine.require_cuda()
+        needs_grad = torch.is_grad_enabled() and (
+            any(t.requires_grad for x in init.x0 for t in x) or
+            any(v.requires_grad for sl in init.slots for v in sl.values()))
+        topo, extras = planning.build_topology(self, init, rplan.channel_keys, self.solver,
+                                               self.ckpt_stride if needs_grad else 0)
+        x0 = planning.canonical_x0(init, P)
+        upar, vpar, slot_vary = planning.pack_slots(init, P, dev)
+        topo['slot_vary'] = slot_vary
+        topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
+        plan = engine.Plan(topo)
+        self.last_plan = plan
+
+        # on-device fault re-reduction (replaces the per-step double inversion of simulator.py:526-528)
+        with torch.no_grad():
+            z_re, z_im = planning.split_complex_batch_last(init.Z0)
+            yd_re, yd_im = planning.split_complex_batch_last(init.Ydiag)
+            Bz = z_re.shape[-1]
+            zsub = torch.empty((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, Bz), dtype=torch.float64, device=dev)
+            engine.network_reduce(z_re, z_im, yd_re, yd_im, extras['obs_bus'], extras['gen_bus'], extras['cfg_sets'],
+                                  planning.FAULT_ADMITTANCE, zsub)
+        t1 = _time.time()
+        rec, x_final = StepFunction.apply(plan, P, x0, upar, vpar, zsub)
+        result = rplan.assemble(rec)
+        if self.verbose:
+            torch.cuda.synchronize()
+            print('Dynamic simulation finished in {:.2f} seconds'.format(_time.time() - t1))
+        self.timings = {'prologue_s': t1 - t0}
+        self._publish_final_state(init, x_final)
+        return self.time, result
+
+    def _publish_final_state(self, init, x_final):
+        """Leave the post-run states on the model objects, as the reference's set_state_vector does."""
+        P = self.parallel_sims
+        xf = x_final.detach()
+        names = SynchMachine.STATES
+        for gi, g in enumerate(init.gens):
+            for k, n in enumerate(names):
+                setattr(g, n, torch.complex(xf[gi, k], torch.zeros_like(xf[gi, k])).reshape(P, 1))
+            if g.exciter:
+                g.exciter.lead_lag.state_1 = xf[gi, 6].reshape(P, 1)
+                g.exciter.pt1_lim.state_1 = xf[gi, 7].reshape(P, 1)
+            if g.governor:
+                g.governor.pt1_lim.state_1 = xf[gi, 8].reshape(P, 1)
+                g.governor.lead_lag.state_1 = xf[gi, 9].reshape(P, 1)
+            if g.stabilizer:
+                g.stabilizer.washout.state_1 = xf[gi, 10].reshape(P, 1)
+                g.stabilizer.lead_lag1.state_1 = xf[gi, 11].reshape(P, 1)
+                g.stabilizer.lead_lag2.state_1 = xf[gi, 12].reshape(P, 1)
+
+
+Pss = PowerSystemSimulation

@@ -1,0 +1,195 @@
+/*
+ * dps.h -- C ABI of the B200-native DiffPSSi stepping engine (libdps_b200.so).
+ *
+ * The reference (georgkordowich/diffpssi 0.0.3) has no FFI: its hot path is the Python loop
+ * ``for t in self.time`` of PowerSystemSimulation.run() (src/diffpssi/power_sim_lib/simulator.py:523-543)
+ * which calls solver.step() (solvers.py:26/75/143) and the model methods.  This header draws the boundary
+ * SURVEY.md section 8(b) proposes: *after* initialize() (simulator.py:505) and *around the whole loop*
+ * (simulator.py:523-546).  One dps_forward() call integrates every step of every trajectory and fills the
+ * recorder; what each entry point replaces is cited at its declaration.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs.  No C++/torch types cross the boundary.
+ *   - every array argument is a DEVICE pointer unless it is a member of dps_topology (host memory, copied
+ *     by dps_plan_create) or documented as host.
+ *   - arrays are fp64, structure-of-arrays with the batch (parallel_sims) index innermost:
+ *         a[i][p]  ==  a[i * P + p]
+ *   - the caller owns every buffer; the library allocates nothing on the device.
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - return value 0 = success; otherwise dps_last_error() holds a message (thread local).
+ *   - NaN/Inf in the data is not an error: diverged trajectories propagate like they do in the reference.
+ */
+#ifndef DPS_H
+#define DPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPS_ABI_VERSION 1
+
+/* ---- per-generator state layout (canonical: absent controllers keep zero slots) ----------------------------
+ * reference order: machine(6) | exciter(lead-lag, PT1) | governor(PT1, lead-lag) | PSS(washout, LL1, LL2)
+ * (synchronous_machine.py:219-228, exciters.py:99-100, governors.py:102-103, stabilizers.py:102-104)        */
+#define DPS_N_STATES 13
+enum dps_state {
+    DPS_X_OMEGA = 0, DPS_X_DELTA, DPS_X_EQT, DPS_X_EDT, DPS_X_EQST, DPS_X_EDST,
+    DPS_X_AVR_LL, DPS_X_AVR_PT1, DPS_X_GOV_PT1, DPS_X_GOV_LL, DPS_X_PSS_W, DPS_X_PSS_LL1, DPS_X_PSS_LL2
+};
+
+/* ---- recordable per-generator fields: the 13 states (post-step values) followed by the algebraics the
+ * reference keeps on the machine object, which hold the values of the LAST stage evaluation of the step
+ * (simulator.py:540-543; synchronous_machine.py:271-277, 148-156)                                           */
+enum dps_field {
+    DPS_F_PE = 13, DPS_F_ID, DPS_F_IQ, DPS_F_VRE, DPS_F_VIM, DPS_F_EFD, DPS_F_PM,
+    DPS_N_FIELDS
+};
+
+/* ---- per-generator constants ("slots").  Derived on the host from the model parameters with the same
+ * expressions the reference evaluates inside the loop (e.g. inv_2h = 1/(2*h), synchronous_machine.py:159), so
+ * multiplying by them is bit-identical to the reference's ``1 / T * (...)``.                                 */
+#define DPS_N_SLOTS 42
+enum dps_slot {
+    /* machine: synchronous_machine.py:158-164, 256-277 */
+    DPS_S_INV_2H = 0, DPS_S_D, DPS_S_INV_TD0T, DPS_S_XD_XDT, DPS_S_INV_TQ0T, DPS_S_XQ_XQT,
+    DPS_S_INV_TD0ST, DPS_S_XDT_XDST, DPS_S_INV_TQ0ST, DPS_S_XQT_XQST,
+    DPS_S_INV_XDST, DPS_S_INV_XQST, DPS_S_SNR, DPS_S_PM0, DPS_S_EFD0,
+    /* SEXS: exciters.py:102-115, blocks.py:143-150 (PT1Limited), 290/319 (LeadLag) */
+    DPS_S_A_R, DPS_S_A_OMR, DPS_S_A_INV_TB, DPS_S_A_INV_TE, DPS_S_A_K, DPS_S_A_EMIN, DPS_S_A_EMAX,
+    DPS_S_A_VSET, DPS_S_A_BIAS,
+    /* TGOV1: governors.py:105-123 */
+    DPS_S_G_INV_T1, DPS_S_G_GAIN, DPS_S_G_VMIN, DPS_S_G_VMAX, DPS_S_G_R, DPS_S_G_OMR, DPS_S_G_INV_T3,
+    DPS_S_G_DT, DPS_S_G_PREF,
+    /* STAB1: stabilizers.py:106-121, blocks.py:382/413 (Washout), 241 (Limiter) */
+    DPS_S_S_INV_TW, DPS_S_S_KW, DPS_S_S_R1, DPS_S_S_OMR1, DPS_S_S_INV_T3, DPS_S_S_R2, DPS_S_S_OMR2,
+    DPS_S_S_INV_T4, DPS_S_S_HLIM
+};
+
+enum dps_solver { DPS_EULER = 0, DPS_HEUN = 1, DPS_RK4 = 2 };      /* solvers.py:226-230 */
+enum dps_ctrl   { DPS_CTRL_AVR = 1, DPS_CTRL_GOV = 2, DPS_CTRL_PSS = 4 };
+
+enum dps_channel_kind { DPS_CH_GEN = 0, DPS_CH_BUS_VRE = 1, DPS_CH_BUS_VIM = 2 };
+
+typedef struct {
+    int32_t kind;     /* dps_channel_kind */
+    int32_t index;    /* generator index (DPS_CH_GEN) or observed-row index (DPS_CH_BUS_*)  */
+    int32_t field;    /* dps_state / dps_field for DPS_CH_GEN, ignored otherwise             */
+} dps_channel;
+
+/* Host-side description of one run; copied by dps_plan_create (all pointers are HOST memory). */
+typedef struct {
+    int32_t abi_version;      /* DPS_ABI_VERSION */
+    int32_t n_gen;            /* generators, in bus order then model order (solvers.py:84-86) */
+    int32_t solver;           /* dps_solver */
+    int32_t n_steps;          /* T = len(np.arange(0, sim_time, dt)) (simulator.py:78) */
+    double  dt;
+    double  fn;               /* system frequency; d(delta)/dt = omega*2*pi*fn (synchronous_machine.py:160) */
+    const int32_t* ctrl;      /* [n_gen] dps_ctrl bit flags */
+    int32_t n_obs;            /* rows of the reduced impedance matrix: the n_gen generator buses first (generator
+                                 order), then any extra buses whose voltage is recorded */
+    int32_t z_rows;           /* row count  of each Zsub configuration as stored (>= n_obs)  */
+    int32_t z_cols;           /* column count of each Zsub configuration as stored (>= n_gen) */
+    int32_t n_cfg;            /* network configurations; 0 = no fault.  One per distinct set of faulted buses. */
+    const uint8_t* step_cfg;  /* [n_steps] configuration active during step k (ScEvent timing, static_models.py:46,
+                                 simulator.py:524-531, evaluated by the host on the reference's own time grid) */
+    int32_t z_per_sim;        /* 0: Zsub shared by the batch; 1: one Zsub per sim */
+    const int32_t* slot_vary; /* [n_gen*DPS_N_SLOTS]: -1 = uniform (value in upar), else row of vpar */
+    int32_t n_vary;           /* rows of vpar */
+    int32_t n_rec;
+    const dps_channel* rec;   /* [n_rec] recorder selectors */
+    int32_t ckpt_stride;      /* 0 = none; else states are checkpointed every ckpt_stride steps (adjoint) */
+} dps_topology;
+
+typedef struct dps_plan dps_plan;
+
+/* Build / destroy a plan (host object; validates the topology, picks the kernel specialisation). */
+int dps_plan_create(const dps_topology* topo, dps_plan** out);
+int dps_plan_destroy(dps_plan* plan);
+
+/* Number of checkpoints a forward call writes for this plan (0 if ckpt_stride == 0). */
+int64_t dps_n_checkpoints(const dps_plan* plan);
+
+/* Bytes of scratch dps_backward needs for P trajectories (dps_forward needs none). */
+size_t dps_workspace_bytes(const dps_plan* plan, int64_t P);
+
+/*
+ * Fault re-reduction on the device.  Replaces the per-step
+ *     Y = inv(Z); Y[:, b, b] = 1e6; Z = inv(Y)            (simulator.py:526-528)
+ * by one rank-1 (Sherman-Morrison) update per faulted bus, computed once per configuration:
+ *     Z' = Z - f * Z[:,b] Z[b,:],   f = c / (1 + c Z_bb),   c = y_fault - Y_bb
+ * (the diagonal is *set*, not incremented), and gathers the rows/columns the stepper needs.
+ *
+ *   Bz            1 (network shared by the batch) or P
+ *   z_re, z_im    [n_bus][n_bus][Bz]   full Z = inv(Y_dyn) of the un-faulted network
+ *   yd_re, yd_im  [n_bus][Bz]          diagonal of Y_dyn
+ *   obs_bus       HOST [n_obs]  bus index of each observed row (generator buses first)
+ *   gen_bus       HOST [n_gen]  bus index of each generator column
+ *   cfg_ptr       HOST [n_cfg+1], cfg_bus HOST [cfg_ptr[n_cfg]]: faulted buses of each configuration (CSR)
+ *   zsub          out [n_cfg][z_rows][z_cols][2][Bz] with z_rows = n_obs + m_max, z_cols = n_gen + m_max,
+ *                 m_max = max faulted buses in one configuration; entries beyond [n_obs][n_gen] are scratch.
+ */
+int dps_network_reduce(int64_t Bz, int32_t n_bus,
+                       const double* z_re, const double* z_im, const double* yd_re, const double* yd_im,
+                       int32_t n_obs, const int32_t* obs_bus, int32_t n_gen, const int32_t* gen_bus,
+                       int32_t n_cfg, const int32_t* cfg_ptr, const int32_t* cfg_bus,
+                       double y_fault, double* zsub, void* stream);
+
+/*
+ * The time loop.  Replaces simulator.py:523-543 for all P trajectories:
+ * fault switching (ScEvent, via step_cfg), solver.step() (solvers.py) with the model equations
+ * (synchronous_machine.py:138-277, blocks.py, exciters.py, governors.py, stabilizers.py), the network solve
+ * V = Z I (solvers.py:83/102) restricted to generator columns / observed rows, and the recorder
+ * (simulator.py:540-546).
+ *
+ *   x0       [n_gen][DPS_N_STATES][P]       initial states (canonical layout)
+ *   upar     [n_gen][DPS_N_SLOTS]           uniform constants
+ *   vpar     [n_vary][P]                    per-sim constants (may be NULL if n_vary == 0)
+ *   zsub     [n_cfg][z_rows][z_cols][2][Bz] reduced impedance, Bz = z_per_sim ? P : 1
+ *   rec      out [n_rec][n_steps][P]        == the reference's [batch, timestep, value] result viewed as
+ *                                           rec.permute(2,1,0) (same memory order as simulator.py:546)
+ *   x_final  out [n_gen][DPS_N_STATES][P]   states after the last step (may be NULL)
+ *   ckpt     out [n_ckpt][n_gen][DPS_N_STATES][P] state *before* step k*ckpt_stride (NULL if ckpt_stride == 0)
+ */
+int dps_forward(const dps_plan* plan, int64_t P,
+                const double* x0, const double* upar, const double* vpar, const double* zsub,
+                double* rec, double* x_final, double* ckpt, void* stream);
+
+/*
+ * Discrete adjoint of dps_forward (what torch autograd does for the reference in
+ * optimization_lib/ps_optimization.py:212).  Recomputes each checkpoint segment forward, then sweeps it
+ * backwards.  Gradients are with respect to the kernel inputs; the host chains them into the torch graph of
+ * the prologue.  Z is treated as constant (parameters that enter Y_dyn are not differentiable yet).
+ *
+ *   grad_rec  [n_rec][n_steps][P]   dL/d rec
+ *   g_x0      out [n_gen][DPS_N_STATES][P]
+ *   g_upar    out [P][n_gen][DPS_N_SLOTS]   per-sim gradient of the uniform constants (host sums over p when the
+ *                                           parameter really is shared) -- only slots listed in want_upar
+ *   g_vpar    out [n_vary][P]
+ *   want      HOST [n_gen*DPS_N_SLOTS] nonzero where a slot gradient is required
+ *   gslot     out [n_want][P]  gradient of every wanted slot, in the order they appear in `want`
+ */
+int dps_backward(const dps_plan* plan, int64_t P,
+                 const double* upar, const double* vpar, const double* zsub, const double* ckpt,
+                 const double* grad_rec, const double* grad_x_final,
+                 const uint8_t* want, double* g_x0, double* gslot,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement helper: runs a dependent-chain-free DFMA loop on every SM and returns the achieved fp64
+ * TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises.  Used by bench.py as the fp64 roofline denominator
+ * (MEASURED_PEAKS.json has no fp64 entry). */
+int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds);
+
+/* Static information about the specialisation a plan selected (for logs / bench "gpu_launches"). */
+int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_per_block, int32_t* regs_per_thread,
+                  int32_t* g_template);
+
+const char* dps_last_error(void);
+int dps_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPS_H */
