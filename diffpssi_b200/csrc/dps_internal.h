@@ -1,6 +1,8 @@
 // dps_internal.h -- structures shared between the ABI layer (dps_abi.cu) and the kernels.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/dps.h"
 
@@ -34,8 +36,10 @@ struct FwdParams {
 
 int fwd_template_g(int n_gen);
 void fwd_geometry(int g_template, int* threads, int* sims_per_block);
+#ifdef __CUDACC__
 cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, bool vary, cudaStream_t stream,
                            int* regs_query);
+#endif
 
 constexpr int RED_MAX_CFG = 16;      // distinct faulted-bus sets per run
 constexpr int RED_MAX_FAULT = 8;     // simultaneously faulted buses
@@ -51,9 +55,11 @@ struct ReduceParams {
     int cfg_n[RED_MAX_CFG];
     int cfg_bus[RED_MAX_CFG][RED_MAX_FAULT];
 };
+#ifdef __CUDACC__
 cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream);
 
 cudaError_t run_fp64_probe(int iters, double* tflops, double* ms);
+#endif
 
 void set_error(const char* fmt, ...);
 

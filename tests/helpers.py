@@ -1,0 +1,188 @@
+"""Shared test helpers: building simulations from the golden fixtures, the host emulation runner, oracle inputs."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from diffpssi_b200 import Pss, engine, planning
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+EMUL_SRC = os.path.join(ROOT, 'tests', 'host_emul', 'emul.cpp')
+EMUL_LIB = os.path.join(ROOT, 'tests', 'host_emul', 'libdps_emul.so')
+DT = 0.005
+
+
+def load_grid(name):
+    with open(os.path.join(GOLD, 'grids', name + '.json')) as f:
+        return json.load(f)
+
+
+def load_gold(case):
+    return np.load(os.path.join(GOLD, case + '.npz'))
+
+
+def resolve_attr(sim, gen_name, attr):
+    obj = sim.get_generator_by_name(gen_name)
+    parts = attr.split('.')
+    for p in parts[:-1]:
+        obj = getattr(obj, p)
+    return obj, parts[-1]
+
+
+def apply_overrides(sim, overrides, requires_grad=False, complex_leaves=True):
+    """overrides: {(gen name, attr path): array[P]} -> sets [P,1] tensors like the reference examples do
+    (examples/models/ibb_model/ibb_opt.py:48-57).  Returns the leaf tensors."""
+    leaves = {}
+    for (gname, attr), val in overrides.items():
+        obj, name = resolve_attr(sim, gname, attr)
+        arr = np.asarray(val, dtype=np.float64).reshape(-1, 1)
+        is_limit = name in ('limit', 'lim_min', 'lim_max')
+        old = getattr(obj, name)
+        want_c = (torch.is_tensor(old) and old.is_complex()) or (requires_grad and complex_leaves and not is_limit)
+        t = torch.tensor(arr, dtype=torch.complex128 if want_c else torch.float64, device=sim.device,
+                         requires_grad=requires_grad and not is_limit)
+        setattr(obj, name, t)
+        if not is_limit:
+            leaves[(gname, attr)] = t
+    return leaves
+
+
+def gold_overrides(gold):
+    out = {}
+    for key in gold.files:
+        if key.startswith('override/'):
+            _k, gname, attr = key[len('override/'):].split('|')
+            out[(gname, attr)] = gold[key]
+    return out
+
+
+def sim_from_gold(case, grid_name, device=None, requires_grad=False, sim_time=None, P=None, tile=1):
+    """Simulation configured like the golden case (grid, solver, events, per-sim overrides, all golden channels)."""
+    gold = load_gold(case)
+    grid = load_grid(grid_name)
+    P0 = gold['traj'].shape[0]
+    P = (P or P0) * tile
+    t = gold['time']
+    sim = Pss(parallel_sims=P, sim_time=sim_time if sim_time is not None else len(t) * DT, time_step=DT,
+              solver=str(gold['solver']), grid_data=grid, verbose=False, device=device)
+    assert len(sim.time) == len(t) or sim_time is not None
+    for (t0, t1, b) in json.loads(str(gold['events'])):
+        sim.add_sc_event(t0, t1, b)
+    ov = {k: np.tile(v, tile) for k, v in gold_overrides(gold).items()}
+    leaves = apply_overrides(sim, ov, requires_grad=requires_grad)
+    sim.set_record_channels([str(s) for s in gold['names']])
+    return sim, gold, leaves
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# host emulation of the device code (tests/host_emul/emul.cpp)
+# ----------------------------------------------------------------------------------------------------------------------
+def build_emul():
+    deps = [EMUL_SRC] + [os.path.join(ROOT, 'diffpssi_b200', 'csrc', f) for f in
+                         ('dps_model.cuh', 'dps_reduce.cuh', 'dps_internal.h')] + [os.path.join(ROOT, 'include', 'dps.h')]
+    if not os.path.exists(EMUL_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_LIB) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-o', EMUL_LIB, EMUL_SRC])
+    return ctypes.CDLL(EMUL_LIB)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def run_emulated(sim):
+    """sim.run() with the two kernels replaced by their host emulation.  Exercises the real prologue, recorder tracing
+    and planning code of the package.  Returns (result [P,T,n] ndarray, dict of intermediates)."""
+    lib = build_emul()
+    init = sim.initialize()
+    P = sim.parallel_sims
+    rplan = sim._trace_recorder(init)
+    topo, extras = planning.build_topology(sim, init, rplan.channel_keys, sim.solver, 0)
+    x0 = planning.canonical_x0(init, P).detach().cpu().numpy()
+    upar_t, vpar_t, slot_vary = planning.pack_slots(init, P, sim.device)
+    upar = upar_t.detach().cpu().numpy()
+    vpar = vpar_t.detach().cpu().numpy() if vpar_t is not None else None
+    z_re, z_im = (a.detach().cpu().numpy() for a in planning.split_complex_batch_last(init.Z0))
+    yd_re, yd_im = (a.detach().cpu().numpy() for a in planning.split_complex_batch_last(init.Ydiag))
+    Bz = z_re.shape[-1]
+    zsub = np.zeros((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, Bz))
+    ci = ctypes.c_int
+    ptr, flat = [0], []
+    for s in extras['cfg_sets']:
+        flat += list(s)
+        ptr.append(len(flat))
+    lib.emul_network_reduce(ctypes.c_longlong(Bz), len(sim.busses), _p(z_re), _p(z_im), _p(yd_re), _p(yd_im),
+                            len(extras['obs_bus']), (ci * len(extras['obs_bus']))(*extras['obs_bus']),
+                            len(extras['gen_bus']), (ci * len(extras['gen_bus']))(*extras['gen_bus']),
+                            len(extras['cfg_sets']), (ci * len(ptr))(*ptr), (ci * max(len(flat), 1))(*flat),
+                            ctypes.c_double(planning.FAULT_ADMITTANCE), _p(zsub))
+    T, G = topo['n_steps'], topo['n_gen']
+    chans = topo['rec']
+    rec = np.zeros((len(chans), T, P))
+    x_final = np.zeros((G, engine.N_STATES, P))
+    step_cfg = np.asarray(topo['step_cfg'], dtype=np.uint8)
+    flat_ch = [v for c in chans for v in c]
+    lib.emul_forward(G, topo['solver'], T, ctypes.c_double(topo['dt']), ctypes.c_double(topo['fn']),
+                     (ci * G)(*topo['ctrl']), topo['n_obs'], topo['z_rows'], topo['z_cols'], topo['n_cfg'],
+                     _p(step_cfg), topo['z_per_sim'], (ci * len(slot_vary))(*slot_vary), len(chans),
+                     (ci * max(len(flat_ch), 1))(*flat_ch), ctypes.c_longlong(P), _p(x0), _p(upar), _p(vpar),
+                     _p(zsub), _p(rec), _p(x_final))
+    result = rplan.assemble(torch.from_numpy(rec)).numpy()
+    return result, dict(init=init, topo=topo, extras=extras, zsub=zsub, x0=x0, upar=upar, vpar=vpar, rec=rec,
+                        x_final=x_final, slot_vary=slot_vary)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# oracle inputs from a package simulation (same inputs for the CUDA path and the oracle)
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_inputs_from_sim(sim, init):
+    """Raw reference-level parameters, x0 and full Z0 for oracle.run(), read off the package's own objects."""
+    P = sim.parallel_sims
+    G = len(init.gens)
+    raw = np.zeros((G, oracle.N_RAW, P))
+
+    def val(v):
+        if torch.is_tensor(v):
+            v = v.detach().cpu()
+            v = (v.real if v.is_complex() else v).numpy().reshape(-1)
+            return v if v.shape[0] == P else np.full(P, v[0])
+        return np.full(P, float(v))
+
+    for gi, g in enumerate(init.gens):
+        def put(name, v):
+            raw[gi, oracle.RAW_INDEX[name]] = val(v)
+        for attr in ('h', 'd', 'x_d', 'x_q', 'x_d_t', 'x_q_t', 'x_d_st', 'x_q_st', 't_d0_t', 't_q0_t', 't_d0_st',
+                     't_q0_st', 's_n'):
+            put(attr, getattr(g, attr))
+        put('s_n_sys', g.s_n_sys)
+        put('p_m0', init.slots[gi]['pm0'])
+        put('e_fd0', init.slots[gi]['efd0'])
+        for attr, rn in oracle.ATTR_TO_RAW.items():
+            if '.' not in attr:
+                continue
+            head = attr.split('.')[0]
+            if getattr(g, head) is None:
+                continue
+            obj, name = resolve_attr(sim, g.name, attr)
+            put(rn, getattr(obj, name))
+        if g.exciter:
+            put('a_v_set', init.slots[gi]['a_vset'])
+            put('a_bias', init.slots[gi]['a_bias'])
+        if g.governor:
+            put('g_p_ref', init.slots[gi]['g_pref'])
+    x0 = planning.canonical_x0(init, P).detach().cpu().numpy()
+    z0 = init.Z0.detach().cpu().numpy()
+    events = [(e.start_time, e.end_time, e.bus) for e in sim.sc_events]
+    return dict(n_bus=len(sim.busses), gen_bus=list(init.gen_bus), ctrl=list(init.ctrl), raw=raw, x0=x0, z0=z0,
+                events=events, fn=sim.fn)
+
+
+def run_oracle_for(sim, init, rec_channels=None, full=True, threads=None):
+    inp = oracle_inputs_from_sim(sim, init)
+    return oracle.run(inp['n_bus'], inp['gen_bus'], inp['ctrl'], sim.solver, float(sim.time_step), inp['fn'],
+                      sim.time, inp['events'], inp['raw'], inp['x0'], inp['z0'], rec=rec_channels or (), full=full,
+                      busv=full, threads=threads)

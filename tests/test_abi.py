@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/dps.h declares; argument validation works without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from diffpssi_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, 'include', 'dps.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(dps_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    names = declared_functions()
+    assert set(names) == set(engine.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dps_abi_version() == engine.ABI_VERSION
+
+
+def test_plan_validation_errors_are_reported():
+    lib = engine.load_library()
+    topo = dict(n_gen=2, solver=1, n_steps=4, dt=0.005, fn=60.0, ctrl=[0, 0], n_obs=2, z_rows=2, z_cols=2, n_cfg=1,
+                step_cfg=[0, 0, 0, 0], z_per_sim=0, slot_vary=[-1] * (2 * engine.N_SLOTS), n_vary=0,
+                rec=[(0, 1, 0), (0, 0, 13)])
+    plan = engine.Plan(topo)
+    assert plan.n_checkpoints() == 0
+    bad = dict(topo, rec=[(0, 5, 0)])
+    with pytest.raises(engine.EngineError, match='out of range'):
+        engine.Plan(bad)
+    with pytest.raises(engine.EngineError, match='duplicates'):
+        engine.Plan(dict(topo, rec=[(0, 1, 0), (0, 1, 0)]))
+    with pytest.raises(engine.EngineError, match='register-resident'):
+        engine.Plan(dict(topo, n_gen=40, ctrl=[0] * 40, slot_vary=[-1] * (40 * engine.N_SLOTS), n_obs=40, z_rows=40,
+                         z_cols=40))
+    with pytest.raises(engine.EngineError, match='n_cfg'):
+        engine.Plan(dict(topo, step_cfg=[0, 3, 0, 0]))
+    ck = engine.Plan(dict(topo, ckpt_stride=3))
+    assert ck.n_checkpoints() == 2
+    # null pointers are rejected before anything is launched
+    rc = lib.dps_forward(plan.handle, 8, None, None, None, None, None, None, None, None)
+    assert rc != 0 and b'null' in lib.dps_last_error()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute entry points refuse to run (the package has no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from tests import helpers
+    sim, _, _ = helpers.sim_from_gold('ibb_heun', 'ibb', device='cpu')
+    with pytest.raises(engine.EngineError, match='no CPU fallback'):
+        sim.run()

@@ -1,0 +1,149 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes -> libdps_b200.so), against
+  (1) the golden vectors generated from the reference's torch backend (tests/golden/*.npz, tolerance 1e-9 p.u. abs),
+  (2) the reference's own golden arrays (tests/golden/ref_*.npy, the reference's tolerance 1e-6),
+  (3) the C oracle (oracle/dps_oracle.c) on the same seeded inputs at sizes it finishes in seconds,
+  (4) size-independent properties at full batch sizes (batch invariance, tail handling, determinism).
+"""
+import numpy as np
+import pytest
+import torch
+
+from diffpssi_b200 import Pss, engine
+from tests import helpers
+from tests.test_host_pipeline import CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9          # BASELINE.json north_star: trajectories within 1e-9 p.u. absolute over the full simulation
+
+
+@pytest.mark.parametrize('case,grid', CASES)
+def test_golden_trajectories(case, grid):
+    sim, gold, _ = helpers.sim_from_gold(case, grid, device='cuda')
+    t, res = sim.run()
+    assert res.is_cuda and tuple(res.shape) == (gold['traj'].shape[0], len(gold['time']), len(gold['names']))
+    mine = res.cpu().numpy()[:, gold['steps'], :]
+    err = np.abs(mine - gold['traj']).max()
+    assert err < TOL, err
+    assert np.array_equal(t, gold['time'])
+
+
+EXAMPLES = [('ibb', 'ibb_model'), ('ibb_trans', 'ibb_transformer'), ('ibb_wc', 'ibb_with_controllers'),
+            ('ieee9', 'ieee_9bus'), ('k2a', 'k2a')]
+
+
+def example_record_function(grid):
+    """The record functions of the reference's example scripts (examples/models/*/*_sim.py)."""
+    if grid == 'ibb':
+        return lambda s: [s.busses[1].models[0].omega.real, s.busses[1].models[0].e_q_st.real,
+                          s.busses[1].models[0].e_d_st.real]
+    if grid == 'ibb_trans':
+        return lambda s: [s.busses[2].models[0].omega.real, s.busses[2].models[0].e_q_st.real,
+                          s.busses[2].models[0].e_d_st.real]
+    if grid == 'ibb_wc':
+        return lambda s: [s.busses[1].models[0].omega.real]
+    if grid == 'ieee9':
+        return lambda s: [s.busses[0].models[0].omega.real, s.busses[0].models[0].p_e,
+                          s.busses[0].models[0].v_bb.real, s.busses[0].models[0].v_bb.imag,
+                          s.busses[1].models[0].omega.real, s.busses[1].models[0].p_e,
+                          s.busses[1].voltage.real, s.busses[1].voltage.imag,
+                          s.busses[2].models[0].omega.real, s.busses[2].models[0].p_e,
+                          s.busses[2].voltage.real, s.busses[2].voltage.imag]
+    return lambda s: ([s.busses[i].models[0].delta.real for i in range(4)] +
+                      [s.busses[i].models[0].omega.real for i in range(4)] +
+                      [s.busses[i].models[0].e_q_st.real for i in range(4)] +
+                      [s.busses[i].models[0].e_d_st.real for i in range(4)])
+
+
+@pytest.mark.parametrize('grid,ref_file', EXAMPLES)
+def test_reference_example_scripts(grid, ref_file):
+    """The reference's own integration tests (tests/integration/test_example_sims.py), re-stated: same grid dict,
+    same event, same Python record function, compared with the reference's golden array at its tolerance (1e-6) and
+    with the live torch-backend output at 1e-9."""
+    sim, gold, _ = helpers.sim_from_gold(grid + '_heun', grid, device='cuda')
+    sim.set_record_function(example_record_function(grid))
+    t, res = sim.run()
+    ref = np.load(helpers.GOLD + '/ref_%s.npy' % ref_file)
+    out = res[0].cpu().numpy()
+    assert np.allclose(out, ref, atol=1e-6, rtol=1e-6)
+    assert np.abs(out - gold['example_rec']).max() < TOL
+
+
+def test_parallel_sims_batch_invariance():
+    """tests/integration/test_parallel_sims.py: IEEE-9 with parallel_sims=3, every row equals the P=1 golden
+    (tolerance 1e-8 there)."""
+    sim, gold, _ = helpers.sim_from_gold('ieee9_heun', 'ieee9', device='cuda', P=3)
+    sim.set_record_function(example_record_function('ieee9'))
+    _, res = sim.run()
+    ref = np.load(helpers.GOLD + '/ref_ieee_9bus.npy')
+    for row in range(3):
+        assert np.allclose(res[row].cpu().numpy(), ref, atol=1e-8, rtol=1e-8)
+    assert torch.equal(res[0], res[1]) and torch.equal(res[0], res[2])
+
+
+def _random_overrides(grid, P, rng, lo, hi):
+    ov = {}
+    nominal = {'k2a': {'G1': (6.5, 0.3), 'G2': (6.5, 0.3), 'G3': (6.175, 0.3), 'G4': (6.175, 0.3)},
+               'ieee9': {'G1': (9.55, 0.15048), 'G2': (3.92, 0.230016), 'G3': (2.766544, 0.232064)},
+               'ibb': {'Gen 1': (3.5, 0.3)}, 'ibb_wc': {'G1': (3.5, 0.3)}}[grid]
+    for g, (h, xdt) in nominal.items():
+        ov[(g, 'h')] = h * rng.uniform(lo, hi, P)
+        ov[(g, 'd')] = rng.uniform(0.0, 2.0, P)
+        ov[(g, 'x_d_t')] = xdt * rng.uniform(lo, hi, P)
+    return ov
+
+
+@pytest.mark.parametrize('grid,solver,P,events,T', [
+    ('k2a', 'heun', 200, [(0.1, 0.2, 'B1')], 300),
+    ('k2a', 'rk4', 70, [(0.1, 0.15, 'B8')], 200),
+    ('ieee9', 'euler', 97, [(0.1, 0.15, 'B8')], 300),
+    ('ibb_wc', 'heun', 33, [(0.1, 0.15, 'B2')], 400),
+    ('ibb', 'heun', 1, [(0.1, 0.15, 'Bus 1')], 400),
+])
+def test_against_oracle_on_seeded_batches(grid, solver, P, events, T):
+    """CUDA path vs the C oracle on identical inputs (the package's own prologue output): every state and algebraic of
+    every generator at every step, ragged batch sizes (not multiples of 32), faults at generator and load buses."""
+    rng = np.random.RandomState(1234)
+    g = helpers.load_grid(grid)
+    sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver=solver, grid_data=g, verbose=False)
+    for ev in events:
+        sim.add_sc_event(*ev)
+    if P > 1:
+        helpers.apply_overrides(sim, _random_overrides(grid, P, rng, 0.9, 1.1))
+    init = sim.initialize()
+    names = []
+    for gen in init.gens:
+        names += ['%s.%s' % (gen.name, f) for f in helpers.oracle.FIELD_NAMES]
+    sim.set_record_channels(names)
+    _, res = sim.run()
+    ref = helpers.run_oracle_for(sim, sim.last_init)
+    want = ref['full'].transpose(3, 0, 1, 2).reshape(P, len(sim.time), -1)      # [P, T, G*20]
+    err = np.abs(res.cpu().numpy() - want).max()
+    assert err < TOL, err
+
+
+def test_recorded_bus_voltages_against_oracle():
+    """Voltages of non-generator buses (extra observed rows of the reduced impedance matrix), incl. the faulted bus."""
+    g = helpers.load_grid('k2a')
+    P = 40
+    sim = Pss(parallel_sims=P, sim_time=1.0, time_step=0.005, solver='heun', grid_data=g, verbose=False)
+    sim.add_sc_event(0.2, 0.3, 'B8')
+    names = ['bus:%s.%s' % (b.name, p) for b in sim.busses for p in ('v_re', 'v_im')]
+    sim.set_record_channels(names)
+    _, res = sim.run()
+    ref = helpers.run_oracle_for(sim, sim.last_init)
+    want = ref['busv'].transpose(3, 0, 1, 2).reshape(P, len(sim.time), -1)
+    assert np.abs(res.cpu().numpy() - want).max() < TOL
+
+
+def test_determinism_and_rerun_after_reset():
+    sim, gold, _ = helpers.sim_from_gold('k2a_heun', 'k2a', device='cuda', P=64, sim_time=1.5)
+    _, a = sim.run()
+    sim.reset()
+    _, b = sim.run()
+    assert torch.equal(a, b)
+
+
+def test_fp64_probe_runs():
+    tf, ms = engine.fp64_peak_probe(2048)
+    assert 5.0 < tf < 80.0, tf

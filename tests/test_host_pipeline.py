@@ -1,0 +1,106 @@
+"""CPU checks of the host side of the package (grid building, torch prologue, recorder tracing, planning/packing) and
+of the device model code compiled for the host (tests/host_emul/emul.cpp), against the golden vectors produced by the
+reference's torch backend.  No GPU, no oracle import in the product: see tests/helpers.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffpssi_b200 import Pss, planning, prologue, recording
+from tests import helpers
+
+CASES = [(g + '_' + s, g) for g in ('ibb', 'ibb_trans', 'ibb_wc', 'ieee9', 'k2a') for s in ('heun', 'euler', 'rk4')]
+CASES += [('k2a_batch_heun', 'k2a'), ('ieee9_persimz_heun', 'ieee9'), ('ieee9_two_events_heun', 'ieee9'),
+          ('k2a_two_events_rk4', 'k2a')]
+
+
+@pytest.mark.parametrize('case,grid', CASES)
+def test_prologue_matches_reference_initialize(case, grid):
+    """x0, held constants and Z0 after initialize() equal the reference's (simulator.py:438-450) to round-off."""
+    sim, gold, _ = helpers.sim_from_gold(case, grid, device='cpu')
+    init = sim.initialize()
+    z0 = init.Z0.numpy()
+    assert np.abs(z0 - gold['init/Z0'][:z0.shape[0]]).max() < 1e-13
+    for g, x0, sl in zip(init.gens, init.x0, init.slots):
+        ref = gold['init/gen:%s.x0' % g.name]                                    # [P, s]
+        mine = np.stack([np.broadcast_to(v.detach().numpy().reshape(-1), (ref.shape[0],)) for v in x0], axis=1)
+        assert np.abs(mine - ref).max() < 1e-13
+        assert np.abs(sl['pm0'].detach().numpy().reshape(-1) - gold['init/gen:%s.p_m' % g.name]).max() < 1e-13
+        assert np.abs(sl['efd0'].detach().numpy().reshape(-1) - gold['init/gen:%s.e_fd' % g.name]).max() < 1e-13
+
+
+@pytest.mark.parametrize('case,grid', CASES)
+def test_emulated_pipeline_matches_reference(case, grid):
+    """prologue -> planning -> (host build of the device code) reproduces every state, algebraic and bus voltage of the
+    reference torch path to 1e-9."""
+    sim, gold, _ = helpers.sim_from_gold(case, grid, device='cpu')
+    result, _ = helpers.run_emulated(sim)
+    mine = result[:, gold['steps'], :]
+    err = np.abs(mine - gold['traj']).max()
+    assert err < 1e-9, err
+
+
+def test_event_schedule_quirks():
+    """Fault timing on the np.arange grid: (1, 1.05) -> steps 201..210, (1, 1.1) -> 201..220, and the
+    multi-event `else` cancellation of simulator.py:524-531."""
+    from diffpssi_b200.components import ScEvent
+    t = np.arange(0, 10, 0.005)
+    cfg, sets = planning.event_schedule(t, [ScEvent(1, 1.05, 3)])
+    assert list(np.nonzero(cfg)[0]) == list(range(201, 211)) and sets == [(), (3,)]
+    cfg, sets = planning.event_schedule(t, [ScEvent(1, 1.1, 0)])
+    assert list(np.nonzero(cfg)[0]) == list(range(201, 221))
+    # later inactive event cancels an earlier active one; later active one survives
+    cfg, sets = planning.event_schedule(t, [ScEvent(0.5, 0.6, 7), ScEvent(0.55, 0.7, 4)])
+    active = {k: sets[c] for k, c in enumerate(cfg) if c}
+    assert all(active[k] == (4, 7) for k in range(111, 121))       # both active: faults at 7 then 4
+    # first inactive (wipes), second active; t[140] = 0.7000000000000001 > 0.7 on the float grid, so 139 is the last
+    assert all(active[k] == (4,) for k in range(121, 140))
+    assert all(k not in active for k in range(101, 111))           # first active, second inactive -> wiped
+    assert min(active) == 111 and max(active) == 139
+
+
+def test_record_function_tracing():
+    grid = helpers.load_grid('ieee9')
+    sim = Pss(parallel_sims=2, sim_time=0.1, time_step=0.005, solver='heun', grid_data=grid, verbose=False, device='cpu')
+
+    def rec(s):          # reference examples/models/ieee_9bus/ieee_9bus_sim.py:20-36
+        return [s.busses[0].models[0].omega.real, s.busses[0].models[0].p_e, s.busses[0].models[0].v_bb.real,
+                s.busses[1].voltage.imag, s.busses[7].voltage.real,
+                torch.abs(s.busses[7].voltage) * 2.0 + s.busses[2].models[0].h.real]
+
+    init = sim.initialize()
+    rp = recording.trace(sim, init.gens, rec)
+    assert rp.channel_keys[:5] == [('gen', 0, 0), ('gen', 0, 13), ('gen', 0, 16), ('bus', 1, 1), ('bus', 7, 0)]
+    assert ('bus', 7, 1) in rp.channel_keys and not rp.direct
+    obs, chans = planning.observed_rows(init, rp.channel_keys)
+    assert obs == [0, 1, 2, 7]                       # three generator buses + the recorded load bus B8
+    assert chans[3] == (0, 1, 17) and chans[4] == (1, 3, 0)
+    fake = torch.arange(len(rp.channel_keys) * 3 * 2, dtype=torch.float64).reshape(len(rp.channel_keys), 3, 2)
+    out = rp.assemble(fake)
+    assert out.shape == (2, 3, 6)
+    k_re, k_im = rp.channel_keys.index(('bus', 7, 0)), rp.channel_keys.index(('bus', 7, 1))
+    expect = torch.sqrt(fake[k_re] ** 2 + fake[k_im] ** 2) * 2.0 + 2.766544
+    assert torch.allclose(out[:, :, 5], expect.T)
+
+
+def test_uniform_collapse_and_vary_classification():
+    sim, gold, _ = helpers.sim_from_gold('k2a_batch_heun', 'k2a', device='cpu')
+    init = sim.initialize()
+    assert init.Z0.shape[0] == 1                     # H, D, X_d', PSS/AVR gains do not enter Y: network shared
+    upar, vpar, slot_vary = planning.pack_slots(init, sim.parallel_sims, 'cpu')
+    names = prologue.SLOTS
+    vary = {(i // len(names), names[i % len(names)]) for i, v in enumerate(slot_vary) if v >= 0}
+    assert (0, 'inv_2h') in vary and (0, 'd') in vary and (0, 'xd_xdt') in vary and (0, 'xdt_xdst') in vary
+    assert (0, 's_kw') in vary and (1, 'a_k') in vary and (0, 'efd0') in vary
+    assert (0, 'inv_tq0t') not in vary and (3, 's_kw') not in vary
+    sim2, _, _ = helpers.sim_from_gold('ieee9_persimz_heun', 'ieee9', device='cpu')
+    assert sim2.initialize().Z0.shape[0] == sim2.parallel_sims        # x_d'' enters Y: per-sim network
+
+
+def test_backend_argument():
+    with pytest.raises(ValueError):
+        Pss(parallel_sims=1, sim_time=1, time_step=0.005, solver='heun', backend='numpy')
+    with pytest.raises(KeyError):
+        Pss(parallel_sims=1, sim_time=1, time_step=0.005, solver='dopri5')
