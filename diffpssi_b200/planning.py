@@ -86,28 +86,36 @@ def pack_slots(init, P, device):
 
 def observed_rows(init, channel_keys):
     """Rows of the reduced impedance matrix: the generator buses (generator order) then every recorded bus that hosts
-    no generator.  Also rewrites recorder keys into C-ABI channels."""
+    no generator.  Also rewrites recorder keys into (unique) C-ABI channels; ``rows[i]`` is the kernel recorder row
+    that holds key i (two keys can name the same quantity, e.g. ``bus.voltage.real`` and ``gen.v_bb.real``)."""
     gen_bus = list(init.gen_bus)
     first_gen_on_bus = {}
     for gi, b in enumerate(gen_bus):
         first_gen_on_bus.setdefault(b, gi)
     obs_bus = list(gen_bus)
-    chans = []
+    chans, rows = [], []
+
+    def channel(c):
+        if c not in chans:
+            chans.append(c)
+        rows.append(chans.index(c))
+
     for key in channel_keys:
         if key[0] == 'gen':
-            chans.append((engine.CH_GEN, key[1], key[2]))
+            channel((engine.CH_GEN, key[1], key[2]))
         else:
             _, bus, part = key
             if bus in first_gen_on_bus:
-                chans.append((engine.CH_GEN, first_gen_on_bus[bus], FIELD_VIM if part else FIELD_VRE))
+                # a generator bus: its voltage is the v_bb the machine thread already holds
+                channel((engine.CH_GEN, first_gen_on_bus[bus], FIELD_VIM if part else FIELD_VRE))
             else:
                 if bus not in obs_bus[len(gen_bus):]:
                     obs_bus.append(bus)
                 row = len(gen_bus) + obs_bus[len(gen_bus):].index(bus)
-                chans.append((engine.CH_BUS_VIM if part else engine.CH_BUS_VRE, row, 0))
+                channel((engine.CH_BUS_VIM if part else engine.CH_BUS_VRE, row, 0))
     if len(obs_bus) - len(gen_bus) > engine.MAX_EXTRA_OBS:
         raise engine.EngineError('too many recorded non-generator buses')
-    return obs_bus, chans
+    return obs_bus, chans, rows
 
 
 def split_complex_batch_last(z):
@@ -119,7 +127,7 @@ def split_complex_batch_last(z):
 def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
     """-> (topo dict for engine.Plan, dict of host-side extras)."""
     step_cfg, cfg_sets = event_schedule(sim.time, sim.sc_events)
-    obs_bus, chans = observed_rows(init, channel_keys)
+    obs_bus, chans, rows = observed_rows(init, channel_keys)
     G = len(init.gens)
     if G > engine.MAX_G:
         raise engine.EngineError('%d generators: the register-resident stepper handles up to %d' % (G, engine.MAX_G))
@@ -131,5 +139,6 @@ def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
         'step_cfg': step_cfg.tolist(), 'z_per_sim': int(init.Z0.shape[0] > 1), 'rec': chans,
         'ckpt_stride': int(ckpt_stride),
     }
-    extras = {'cfg_sets': cfg_sets, 'obs_bus': obs_bus, 'gen_bus': list(init.gen_bus), 'm_max': m_max}
+    extras = {'cfg_sets': cfg_sets, 'obs_bus': obs_bus, 'gen_bus': list(init.gen_bus), 'm_max': m_max,
+              'key_rows': rows}
     return topo, extras

@@ -254,6 +254,9 @@ class PowerSystemSimulation(object):
                                   planning.FAULT_ADMITTANCE, zsub)
         t1 = _time.time()
         rec, x_final = StepFunction.apply(plan, P, x0, upar, vpar, zsub)
+        rows = extras['key_rows']
+        if rows != list(range(rec.shape[0])):
+            rec = rec[torch.tensor(rows, device=rec.device)]
         result = rplan.assemble(rec)
         if self.verbose:
             torch.cuda.synchronize()

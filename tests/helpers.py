@@ -131,7 +131,7 @@ def run_emulated(sim):
                      _p(step_cfg), topo['z_per_sim'], (ci * len(slot_vary))(*slot_vary), len(chans),
                      (ci * max(len(flat_ch), 1))(*flat_ch), ctypes.c_longlong(P), _p(x0), _p(upar), _p(vpar),
                      _p(zsub), _p(rec), _p(x_final))
-    result = rplan.assemble(torch.from_numpy(rec)).numpy()
+    result = rplan.assemble(torch.from_numpy(rec[extras['key_rows']])).numpy()
     return result, dict(init=init, topo=topo, extras=extras, zsub=zsub, x0=x0, upar=upar, vpar=vpar, rec=rec,
                         x_final=x_final, slot_vary=slot_vary)
 

@@ -74,7 +74,7 @@ def test_record_function_tracing():
     rp = recording.trace(sim, init.gens, rec)
     assert rp.channel_keys[:5] == [('gen', 0, 0), ('gen', 0, 13), ('gen', 0, 16), ('bus', 1, 1), ('bus', 7, 0)]
     assert ('bus', 7, 1) in rp.channel_keys and not rp.direct
-    obs, chans = planning.observed_rows(init, rp.channel_keys)
+    obs, chans, rows = planning.observed_rows(init, rp.channel_keys)
     assert obs == [0, 1, 2, 7]                       # three generator buses + the recorded load bus B8
     assert chans[3] == (0, 1, 17) and chans[4] == (1, 3, 0)
     fake = torch.arange(len(rp.channel_keys) * 3 * 2, dtype=torch.float64).reshape(len(rp.channel_keys), 3, 2)
