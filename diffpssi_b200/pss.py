@@ -223,11 +223,12 @@ class PowerSystemSimulation(object):
             raise TypeError('No record function specified')
         return recording.trace(self, init.gens, self.record_func)
 
-    def run(self):
-        """Initialise, integrate every step of every trajectory on the GPU, return (time, result[P,T,n])."""
+    def prepare(self):
+        """Everything ``run()`` does before the time loop: prologue, recorder tracing, planning, packing.
+        Returns a :class:`PreparedRun` whose ``launch()`` enqueues the kernels (used by bench.py to time the loop
+        alone, as the reference's own timer does -- simulator.py:507, 548-550)."""
         if self.param_events:
             raise NotImplementedError('ParamEvent scheduling is not part of this round (SURVEY.md section 8f.3)')
-        t0 = _time.time()
         init = self.initialize()
         P, dev = self.parallel_sims, self.device
         rplan = self._trace_recorder(init)
@@ -243,26 +244,24 @@ class PowerSystemSimulation(object):
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         plan = engine.Plan(topo)
         self.last_plan = plan
-
-        # on-device fault re-reduction (replaces the per-step double inversion of simulator.py:526-528)
         with torch.no_grad():
             z_re, z_im = planning.split_complex_batch_last(init.Z0)
             yd_re, yd_im = planning.split_complex_batch_last(init.Ydiag)
-            Bz = z_re.shape[-1]
-            zsub = torch.empty((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, Bz), dtype=torch.float64, device=dev)
-            engine.network_reduce(z_re, z_im, yd_re, yd_im, extras['obs_bus'], extras['gen_bus'], extras['cfg_sets'],
-                                  planning.FAULT_ADMITTANCE, zsub)
+            zsub = torch.empty((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, z_re.shape[-1]),
+                               dtype=torch.float64, device=dev)
+        return PreparedRun(self, init, rplan, plan, topo, extras, x0, upar, vpar, (z_re, z_im, yd_re, yd_im), zsub)
+
+    def run(self):
+        """Initialise, integrate every step of every trajectory on the GPU, return (time, result[P,T,n])."""
+        t0 = _time.time()
+        prep = self.prepare()
         t1 = _time.time()
-        rec, x_final = StepFunction.apply(plan, P, x0, upar, vpar, zsub)
-        rows = extras['key_rows']
-        if rows != list(range(rec.shape[0])):
-            rec = rec[torch.tensor(rows, device=rec.device)]
-        result = rplan.assemble(rec)
+        result, x_final = prep.execute()
         if self.verbose:
             torch.cuda.synchronize()
             print('Dynamic simulation finished in {:.2f} seconds'.format(_time.time() - t1))
         self.timings = {'prologue_s': t1 - t0}
-        self._publish_final_state(init, x_final)
+        self._publish_final_state(prep.init, x_final)
         return self.time, result
 
     def _publish_final_state(self, init, x_final):
@@ -283,6 +282,36 @@ class PowerSystemSimulation(object):
                 g.stabilizer.washout.state_1 = xf[gi, 10].reshape(P, 1)
                 g.stabilizer.lead_lag1.state_1 = xf[gi, 11].reshape(P, 1)
                 g.stabilizer.lead_lag2.state_1 = xf[gi, 12].reshape(P, 1)
+
+
+class PreparedRun(object):
+    """Device-resident inputs of one run plus the two kernel launches of the time loop."""
+
+    def __init__(self, sim, init, rplan, plan, topo, extras, x0, upar, vpar, zparts, zsub):
+        self.sim, self.init, self.rplan, self.plan, self.topo, self.extras = sim, init, rplan, plan, topo, extras
+        self.x0, self.upar, self.vpar, self.zparts, self.zsub = x0, upar, vpar, zparts, zsub
+        self.kernels_per_launch = 2          # dps_network_reduce_kernel + dps_step_kernel
+
+    def reduce_network(self):
+        """On-device fault re-reduction (replaces the per-step double inversion of simulator.py:526-528)."""
+        z_re, z_im, yd_re, yd_im = self.zparts
+        engine.network_reduce(z_re, z_im, yd_re, yd_im, self.extras['obs_bus'], self.extras['gen_bus'],
+                              self.extras['cfg_sets'], planning.FAULT_ADMITTANCE, self.zsub)
+
+    def launch(self, rec, x_final=None):
+        """Raw, autograd-free time loop into caller-provided buffers (both kernels, current stream)."""
+        self.reduce_network()
+        self.plan.forward(self.sim.parallel_sims, self.x0.detach(), self.upar.detach(),
+                          None if self.vpar is None else self.vpar.detach(), self.zsub, rec, x_final, None)
+
+    def execute(self):
+        with torch.no_grad():
+            self.reduce_network()
+        rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, self.zsub)
+        rows = self.extras['key_rows']
+        if rows != list(range(rec.shape[0])):
+            rec = rec[torch.tensor(rows, device=rec.device)]
+        return self.rplan.assemble(rec), x_final
 
 
 Pss = PowerSystemSimulation

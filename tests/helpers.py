@@ -136,53 +136,4 @@ def run_emulated(sim):
                         x_final=x_final, slot_vary=slot_vary)
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-# oracle inputs from a package simulation (same inputs for the CUDA path and the oracle)
-# ----------------------------------------------------------------------------------------------------------------------
-def oracle_inputs_from_sim(sim, init):
-    """Raw reference-level parameters, x0 and full Z0 for oracle.run(), read off the package's own objects."""
-    P = sim.parallel_sims
-    G = len(init.gens)
-    raw = np.zeros((G, oracle.N_RAW, P))
-
-    def val(v):
-        if torch.is_tensor(v):
-            v = v.detach().cpu()
-            v = (v.real if v.is_complex() else v).numpy().reshape(-1)
-            return v if v.shape[0] == P else np.full(P, v[0])
-        return np.full(P, float(v))
-
-    for gi, g in enumerate(init.gens):
-        def put(name, v):
-            raw[gi, oracle.RAW_INDEX[name]] = val(v)
-        for attr in ('h', 'd', 'x_d', 'x_q', 'x_d_t', 'x_q_t', 'x_d_st', 'x_q_st', 't_d0_t', 't_q0_t', 't_d0_st',
-                     't_q0_st', 's_n'):
-            put(attr, getattr(g, attr))
-        put('s_n_sys', g.s_n_sys)
-        put('p_m0', init.slots[gi]['pm0'])
-        put('e_fd0', init.slots[gi]['efd0'])
-        for attr, rn in oracle.ATTR_TO_RAW.items():
-            if '.' not in attr:
-                continue
-            head = attr.split('.')[0]
-            if getattr(g, head) is None:
-                continue
-            obj, name = resolve_attr(sim, g.name, attr)
-            put(rn, getattr(obj, name))
-        if g.exciter:
-            put('a_v_set', init.slots[gi]['a_vset'])
-            put('a_bias', init.slots[gi]['a_bias'])
-        if g.governor:
-            put('g_p_ref', init.slots[gi]['g_pref'])
-    x0 = planning.canonical_x0(init, P).detach().cpu().numpy()
-    z0 = init.Z0.detach().cpu().numpy()
-    events = [(e.start_time, e.end_time, e.bus) for e in sim.sc_events]
-    return dict(n_bus=len(sim.busses), gen_bus=list(init.gen_bus), ctrl=list(init.ctrl), raw=raw, x0=x0, z0=z0,
-                events=events, fn=sim.fn)
-
-
-def run_oracle_for(sim, init, rec_channels=None, full=True, threads=None):
-    inp = oracle_inputs_from_sim(sim, init)
-    return oracle.run(inp['n_bus'], inp['gen_bus'], inp['ctrl'], sim.solver, float(sim.time_step), inp['fn'],
-                      sim.time, inp['events'], inp['raw'], inp['x0'], inp['z0'], rec=rec_channels or (), full=full,
-                      busv=full, threads=threads)
+from oracle.adapter import oracle_inputs_from_sim, run_oracle_for  # noqa: E402,F401
