@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "dps_internal.h"
+#include "dps_plan.h"
 
 namespace dps {
 
@@ -24,17 +25,6 @@ void set_error(const char* fmt, ...) {
 
 using namespace dps;
 
-struct dps_plan {
-    dps_topology topo;                    // scalar members valid; pointers re-targeted to the vectors below
-    std::vector<int32_t> ctrl;
-    std::vector<uint8_t> step_cfg;
-    std::vector<int32_t> slot_vary;
-    std::vector<dps_channel> rec;
-    std::vector<int> seg_step, seg_cfg;   // configuration change points
-    int g_template;
-    bool any_ctrl, any_vary;
-    FwdParams base;                       // everything that does not depend on the call
-};
 
 extern "C" {
 
@@ -81,11 +71,16 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
         if (v >= t->n_vary) { set_error("dps_plan_create: slot_vary entry %d >= n_vary %d", v, t->n_vary); delete pl; return 1; }
         pl->any_vary |= (v >= 0);
     }
+    // fast path: only the DPS_N_REG_SLOTS leading constants may differ between trajectories
+    pl->pmode = 1;
+    for (int g = 0; g < t->n_gen; ++g)
+        for (int k = DPS_N_REG_SLOTS; k < DPS_N_SLOTS; ++k)
+            if (pl->slot_vary[(size_t)g * DPS_N_SLOTS + k] >= 0) pl->pmode = 2;
 
     FwdParams& b = pl->base;
     memset(&b, 0, sizeof(b));
     b.n_gen = t->n_gen; b.solver = t->solver; b.n_steps = t->n_steps; b.dt = t->dt; b.fn = t->fn;
-    b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.z_per_sim = t->z_per_sim;
+    b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.n_cfg = t->n_cfg; b.z_per_sim = t->z_per_sim;
     b.ckpt_stride = t->ckpt_stride;
     for (int g = 0; g < t->n_gen; ++g) b.ctrl[g] = pl->ctrl[g];
     for (size_t i = 0; i < pl->slot_vary.size(); ++i) b.slot_vary[i] = (short)pl->slot_vary[i];
@@ -136,7 +131,7 @@ int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_pe
     if (g_template) *g_template = plan->g_template;
     if (regs_per_thread) {
         int regs = 0;
-        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->any_ctrl, plan->any_vary, 0, &regs);
+        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->any_ctrl, plan->pmode, 0, &regs);
         if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
         *regs_per_thread = regs;
     }
@@ -170,7 +165,7 @@ int dps_forward(const dps_plan* plan, int64_t P, const double* x0, const double*
         const bool last = (seg1 == n_seg);
         if (!last && !x_final) { set_error("dps_forward: more than %d configuration changes need x_final as carry buffer", MAX_SEG); return 1; }
         p.x_final = x_final;
-        cudaError_t e = launch_forward(p, plan->g_template, plan->any_ctrl, plan->any_vary, st, nullptr);
+        cudaError_t e = launch_forward(p, plan->g_template, plan->any_ctrl, plan->pmode, st, nullptr);
         if (e != cudaSuccess) { set_error("dps_forward: launch failed: %s", cudaGetErrorString(e)); return 3; }
         x_in = x_final;
         seg0 = seg1;

@@ -24,7 +24,7 @@ struct FwdParams {
     double* rec;             // [n_rec][n_steps][P]
     double* x_final;         // [n_gen][13][P] or null
     double* ckpt;            // [n_ckpt][n_gen][13][P] or null
-    int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_seg;
+    int n_obs, z_rows, z_cols, n_cfg, z_per_sim, ckpt_stride, n_seg;
     int seg_step[MAX_SEG];
     int seg_cfg[MAX_SEG];
     int ctrl[MAX_G];
@@ -37,7 +37,7 @@ struct FwdParams {
 int fwd_template_g(int n_gen);
 void fwd_geometry(int g_template, int* threads, int* sims_per_block);
 #ifdef __CUDACC__
-cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, bool vary, cudaStream_t stream,
+cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, int pmode, cudaStream_t stream,
                            int* regs_query);
 #endif
 

@@ -10,6 +10,84 @@
 
 namespace dps {
 
+// ---- math primitives ----------------------------------------------------------------------------------------------
+// Device versions are branch-free (no slow-path subroutine, no local-memory scratch): the kernel is bound by the FP64
+// pipe and by issue slots, and the CUDA library versions of sincos / division / sqrt each carry a divergent slow path.
+// Accuracy is ~1 ulp, far inside the 1e-9 p.u. parity budget.  The host versions (used only by the CPU emulation in
+// tests/host_emul) call libm.
+#ifdef __CUDACC__
+// fdlibm kernel coefficients (k_sin.c / k_cos.c) and the Cody-Waite split of pi/2 (e_rem_pio2.c); kept in constant
+// memory so each DFMA takes its coefficient as a c[bank][offset] operand instead of two UMOVs.
+static __constant__ double dps_trig_c[16] = {
+    6.36619772367581382433e-01, 6755399441055744.0, 1.57079632673412561417e+00, 6.07710050650619224932e-11,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+#endif
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double dps_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);                   // two Newton steps: 2^-20 -> 2^-40 -> 2^-80
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double dps_div(double a, double b) {
+    const double r = dps_rcp(b);
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);             // one residual correction
+}
+__device__ __forceinline__ double dps_sqrt(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double h = 0.5 * y;
+    double e = fma(-s * y, h, 0.5);                // 0.5 - 0.5*s*y^2
+    y = fma(y, e, y);
+    h = 0.5 * y;
+    e = fma(-s * y, h, 0.5);
+    y = fma(y, e, y);
+    const double r = s * y;
+    const double res = fma(fma(-r, r, s), 0.5 * y, r);
+    return (s > 0.0) ? res : 0.0;
+}
+// sin/cos with 2-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4].
+// Rotor angles stay far below the 1e6 rad where the 2-term reduction starts to lose bits.
+__device__ __forceinline__ void dps_sincos(double x, double* sp, double* cp) {
+    const double* C = dps_trig_c;
+    const double t = fma(x, C[0], C[1]);
+    const int q = __double2loint(t);
+    const double k = t - C[1];
+    double r = fma(-k, C[2], x);
+    r = fma(-k, C[3], r);
+    const double z = r * r;
+    double ps = fma(z, C[4], C[5]);
+    ps = fma(z, ps, C[6]);
+    ps = fma(z, ps, C[7]);
+    ps = fma(z, ps, C[8]);
+    ps = fma(z, ps, C[9]);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, C[10], C[11]);
+    pc = fma(z, pc, C[12]);
+    pc = fma(z, pc, C[13]);
+    pc = fma(z, pc, C[14]);
+    pc = fma(z, pc, C[15]);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    double s = (q & 1) ? cr : sr;
+    double c = (q & 1) ? sr : cr;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+    *sp = s;
+    *cp = c;
+}
+#else
+inline double dps_rcp(double x) { return 1.0 / x; }
+inline double dps_div(double a, double b) { return a / b; }
+inline double dps_sqrt(double s) { return sqrt(s); }
+inline void dps_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+#endif
+
 // Reads constant `slot` of the generator this thread works on.  UP = uniform table in shared memory,
 // VARY=true adds the per-sim override path.
 template <bool VARY>
@@ -24,6 +102,19 @@ struct ParamReader {
             if (vi >= 0) return __ldg(vpar + (long long)vi * P + s);
         }
         return up[slot];
+    }
+};
+
+// Fast-path reader: the DPS_N_REG_SLOTS leading constants of this (trajectory, generator) -- the 15 machine constants
+// (what parameter identification varies per sim: H, D, X_d, X_q, X_d', X_q', ...) and the three controller set points
+// initialize() derives from them -- live in registers; the remaining controller constants are uniform and come
+// from shared memory as warp-broadcast loads at compile-time offsets.  `slot` is a literal at every call site, so the
+// branch folds away.
+struct ParamRegs {
+    const double* pm;        // registers, [DPS_N_REG_SLOTS]
+    const double* up;        // shared memory, [DPS_N_SLOTS] uniform constants of this generator
+    __device__ __forceinline__ double operator()(int slot) const {
+        return (slot < DPS_N_REG_SLOTS) ? pm[slot] : up[slot];
     }
 };
 
@@ -46,7 +137,10 @@ __device__ __forceinline__ void injection(const double* x, const PR& par, double
 }
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) {
-    return fmin(fmax(v, lo), hi);      // blocks.py:181, 241: minimum(maximum(x.real, lo), hi)
+    // blocks.py:181, 241: minimum(maximum(x.real, lo), hi).  Written as compare+select: the library fmin/fmax expand to
+    // ~8 integer instructions each for their NaN rules (a NaN state stays NaN here, as it does in torch).
+    const double m = (v < lo) ? lo : v;
+    return (m > hi) ? hi : m;
 }
 
 // Anti-windup gate of PT1Limited.differential, blocks.py:145-149: `<=`/`>=` on the state, strict on the derivative
@@ -102,7 +196,7 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
         }
         if (ctrl & DPS_CTRL_AVR) {
             // SEXS.get_output(|v_bb| - v_pss), exciters.py:111-114
-            const double v_abs = sqrt(v_re * v_re + v_im * v_im);
+            const double v_abs = dps_sqrt(v_re * v_re + v_im * v_im);
             const double sig = (ctrl & DPS_CTRL_PSS) ? (v_abs - v_pss) : v_abs;
             const double u = (par(DPS_S_A_VSET) - sig) + par(DPS_S_A_BIAS);
             const double xll = x[DPS_X_AVR_LL], xe = x[DPS_X_AVR_PT1];
@@ -128,7 +222,7 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
     }
 
     // synchronous_machine.py:158-164
-    const double t_m = p_m / (1.0 + omega);
+    const double t_m = dps_div(p_m, 1.0 + omega);
     f[DPS_X_OMEGA] = par(DPS_S_INV_2H) * ((t_m - p_e) - par(DPS_S_D) * omega);
     f[DPS_X_DELTA] = ((omega * 2.0) * 3.141592653589793) * fn;
     f[DPS_X_EQT] = par(DPS_S_INV_TD0T) * ((e_fd - x[DPS_X_EQT]) - i_d * par(DPS_S_XD_XDT));

@@ -1,0 +1,17 @@
+// dps_plan.h -- the host-side plan object behind the opaque ``dps_plan*`` of include/dps.h.
+#pragma once
+#include <vector>
+#include "dps_internal.h"
+
+struct dps_plan {
+    dps_topology topo;                    // scalar members valid; pointers re-targeted to the vectors below
+    std::vector<int32_t> ctrl;
+    std::vector<uint8_t> step_cfg;
+    std::vector<int32_t> slot_vary;
+    std::vector<dps_channel> rec;
+    std::vector<int> seg_step, seg_cfg;   // configuration change points
+    int g_template;
+    bool any_ctrl, any_vary;
+    int pmode;                            // 1 = machine constants in registers, 2 = generic slot table
+    dps::FwdParams base;                       // everything that does not depend on the call
+};

@@ -38,13 +38,17 @@ SLOTS = (
     # machine (synchronous_machine.py:158-164, 256-277)
     'inv_2h', 'd', 'inv_td0t', 'xd_xdt', 'inv_tq0t', 'xq_xqt', 'inv_td0st', 'xdt_xdst', 'inv_tq0st', 'xqt_xqst',
     'inv_xdst', 'inv_xqst', 'snr', 'pm0', 'efd0',
+    # controller constants derived from the machine's initial state (exciters.py:137-138, simulator.py:319,
+    # governors.py:145): per-sim whenever a machine parameter is
+    'a_vset', 'a_bias', 'g_pref',
     # SEXS (exciters.py:102-115; blocks.py:143-150, 290, 319)
-    'a_r', 'a_omr', 'a_inv_tb', 'a_inv_te', 'a_k', 'a_emin', 'a_emax', 'a_vset', 'a_bias',
+    'a_r', 'a_omr', 'a_inv_tb', 'a_inv_te', 'a_k', 'a_emin', 'a_emax',
     # TGOV1 (governors.py:105-123)
-    'g_inv_t1', 'g_gain', 'g_vmin', 'g_vmax', 'g_r', 'g_omr', 'g_inv_t3', 'g_dt', 'g_pref',
+    'g_inv_t1', 'g_gain', 'g_vmin', 'g_vmax', 'g_r', 'g_omr', 'g_inv_t3', 'g_dt',
     # STAB1 (stabilizers.py:106-121; blocks.py:382, 413, 241)
     's_inv_tw', 's_kw', 's_r1', 's_omr1', 's_inv_t3', 's_r2', 's_omr2', 's_inv_t4', 's_hlim',
 )
+N_REG_SLOTS = 18        # leading slots the fast kernel keeps in registers (DPS_N_REG_SLOTS)
 SLOT_INDEX = {n: i for i, n in enumerate(SLOTS)}
 N_SLOTS = len(SLOTS)
 

@@ -17,7 +17,7 @@ import time as _time
 import numpy as np
 import torch
 
-from . import engine, planning, prologue, recording
+from . import adjoint, engine, planning, prologue, recording
 from .autograd import StepFunction
 from .components import (Bus, Line, Transformer, Load, Shunt, SynchMachine, SEXS, TGOV1, STAB1, ScEvent,
                          ParamEvent)
@@ -232,7 +232,6 @@ class PowerSystemSimulation(object):
         init = self.initialize()
         P, dev = self.parallel_sims, self.device
         rplan = self._trace_recorder(init)
-        engine.require_cuda()
         needs_grad = torch.is_grad_enabled() and (
             any(t.requires_grad for x in init.x0 for t in x) or
             any(v.requires_grad for sl in init.slots for v in sl.values()))
@@ -242,6 +241,7 @@ class PowerSystemSimulation(object):
         upar, vpar, slot_vary = planning.pack_slots(init, P, dev)
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
+        topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
         plan = engine.Plan(topo)
         self.last_plan = plan
         with torch.no_grad():
@@ -305,6 +305,7 @@ class PreparedRun(object):
                           None if self.vpar is None else self.vpar.detach(), self.zsub, rec, x_final, None)
 
     def execute(self):
+        engine.require_cuda()
         with torch.no_grad():
             self.reduce_network()
         rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, self.zsub)

@@ -52,17 +52,20 @@ enum dps_field {
  * expressions the reference evaluates inside the loop (e.g. inv_2h = 1/(2*h), synchronous_machine.py:159), so
  * multiplying by them is bit-identical to the reference's ``1 / T * (...)``.                                 */
 #define DPS_N_SLOTS 42
+#define DPS_N_REG_SLOTS 18   /* leading slots the fast kernel keeps in registers (may differ per trajectory) */
 enum dps_slot {
     /* machine: synchronous_machine.py:158-164, 256-277 */
     DPS_S_INV_2H = 0, DPS_S_D, DPS_S_INV_TD0T, DPS_S_XD_XDT, DPS_S_INV_TQ0T, DPS_S_XQ_XQT,
     DPS_S_INV_TD0ST, DPS_S_XDT_XDST, DPS_S_INV_TQ0ST, DPS_S_XQT_XQST,
     DPS_S_INV_XDST, DPS_S_INV_XQST, DPS_S_SNR, DPS_S_PM0, DPS_S_EFD0,
+    /* controller constants that initialize() derives from the machine state (exciters.py:137-138, simulator.py:319,
+       governors.py:145): they differ per trajectory whenever a machine parameter does */
+    DPS_S_A_VSET, DPS_S_A_BIAS, DPS_S_G_PREF,
     /* SEXS: exciters.py:102-115, blocks.py:143-150 (PT1Limited), 290/319 (LeadLag) */
     DPS_S_A_R, DPS_S_A_OMR, DPS_S_A_INV_TB, DPS_S_A_INV_TE, DPS_S_A_K, DPS_S_A_EMIN, DPS_S_A_EMAX,
-    DPS_S_A_VSET, DPS_S_A_BIAS,
     /* TGOV1: governors.py:105-123 */
     DPS_S_G_INV_T1, DPS_S_G_GAIN, DPS_S_G_VMIN, DPS_S_G_VMAX, DPS_S_G_R, DPS_S_G_OMR, DPS_S_G_INV_T3,
-    DPS_S_G_DT, DPS_S_G_PREF,
+    DPS_S_G_DT,
     /* STAB1: stabilizers.py:106-121, blocks.py:382/413 (Washout), 241 (Limiter) */
     DPS_S_S_INV_TW, DPS_S_S_KW, DPS_S_S_R1, DPS_S_S_OMR1, DPS_S_S_INV_T3, DPS_S_S_R2, DPS_S_S_OMR2,
     DPS_S_S_INV_T4, DPS_S_S_HLIM

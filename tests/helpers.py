@@ -137,3 +137,81 @@ def run_emulated(sim):
 
 
 from oracle.adapter import oracle_inputs_from_sim, run_oracle_for  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# emulated autograd path (CPU): the package's prepare() + host builds of the forward / adjoint device code
+# ----------------------------------------------------------------------------------------------------------------------
+class EmulStepFunction(torch.autograd.Function):
+    """CPU stand-in for diffpssi_b200.autograd.StepFunction used by the `not gpu` gradient tests."""
+
+    @staticmethod
+    def forward(ctx, prep, x0, upar, vpar, zsub_np):
+        lib = build_emul()
+        topo = prep.topo
+        P = prep.sim.parallel_sims
+        T, G = topo['n_steps'], topo['n_gen']
+        ci = ctypes.c_int
+        chans = topo['rec']
+        flat_ch = [v for c in chans for v in c]
+        args = dict(
+            head=(G, topo['solver'], T, ctypes.c_double(topo['dt']), ctypes.c_double(topo['fn']),
+                  (ci * G)(*topo['ctrl']), topo['n_obs'], topo['z_rows'], topo['z_cols'], topo['n_cfg'],
+                  _p(np.asarray(topo['step_cfg'], dtype=np.uint8)), topo['z_per_sim'],
+                  (ci * len(topo['slot_vary']))(*topo['slot_vary']), len(chans), (ci * max(len(flat_ch), 1))(*flat_ch),
+                  ctypes.c_longlong(P)))
+        x0n = np.ascontiguousarray(x0.detach().numpy())
+        upn = np.ascontiguousarray(upar.detach().numpy())
+        vpn = np.ascontiguousarray(vpar.detach().numpy()) if vpar is not None else None
+        rec = np.zeros((len(chans), T, P))
+        xf = np.zeros((G, engine.N_STATES, P))
+        keep = np.asarray(topo['step_cfg'], dtype=np.uint8)
+        head = list(args['head'])
+        head[10] = _p(keep)
+        lib.emul_forward(*head, _p(x0n), _p(upn), _p(vpn), _p(zsub_np), _p(rec), _p(xf))
+        ctx.saved = (head, keep, x0n, upn, vpn, zsub_np, topo, P)
+        return torch.from_numpy(rec)
+
+    @staticmethod
+    def backward(ctx, g_rec):
+        lib = build_emul()
+        head, keep, x0n, upn, vpn, zsub_np, topo, P = ctx.saved
+        G = topo['n_gen']
+        g = np.ascontiguousarray(g_rec.numpy())
+        g_x0 = np.zeros((G, engine.N_STATES, P))
+        gslot = np.zeros((G, engine.N_SLOTS, P))
+        lib.emul_backward(*head, _p(x0n), _p(upn), _p(vpn), _p(zsub_np), _p(g), _p(g_x0), _p(gslot))
+        g_upar = torch.zeros(upn.shape, dtype=torch.float64)
+        g_vpar = torch.zeros(vpn.shape, dtype=torch.float64) if vpn is not None else None
+        for i, vi in enumerate(topo['slot_vary']):
+            gi, k = divmod(i, engine.N_SLOTS)
+            if vi >= 0:
+                g_vpar[vi] = torch.from_numpy(gslot[gi, k])
+            else:
+                g_upar[gi, k] = float(gslot[gi, k].sum())
+        return None, torch.from_numpy(g_x0), g_upar, g_vpar, None
+
+
+def run_emulated_autograd(sim):
+    """Differentiable CPU run: the package's real prologue graph + emulated kernels.  Returns result [P,T,n] tensor."""
+    prep = sim.prepare()
+    lib = build_emul()
+    topo, extras = prep.topo, prep.extras
+    z_re, z_im, yd_re, yd_im = (a.detach().cpu().numpy() for a in prep.zparts)
+    Bz = z_re.shape[-1]
+    zsub = np.zeros((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, Bz))
+    ci = ctypes.c_int
+    ptr, flat = [0], []
+    for s in extras['cfg_sets']:
+        flat += list(s)
+        ptr.append(len(flat))
+    lib.emul_network_reduce(ctypes.c_longlong(Bz), len(sim.busses), _p(z_re), _p(z_im), _p(yd_re), _p(yd_im),
+                            len(extras['obs_bus']), (ci * len(extras['obs_bus']))(*extras['obs_bus']),
+                            len(extras['gen_bus']), (ci * len(extras['gen_bus']))(*extras['gen_bus']),
+                            len(extras['cfg_sets']), (ci * len(ptr))(*ptr), (ci * max(len(flat), 1))(*flat),
+                            ctypes.c_double(planning.FAULT_ADMITTANCE), _p(zsub))
+    rec = EmulStepFunction.apply(prep, prep.x0, prep.upar, prep.vpar, zsub)
+    rows = extras['key_rows']
+    if rows != list(range(rec.shape[0])):
+        rec = rec[torch.tensor(rows)]
+    return prep.rplan.assemble(rec)

@@ -139,3 +139,147 @@ int emul_forward(int n_gen, int solver, int n_steps, double dt, double fn, const
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------------------
+// host emulation of the adjoint (csrc/dps_adjoint.cuh + the sweep structure of csrc/dps_backward.cu)
+// ----------------------------------------------------------------------------------------------------------------------
+#include "../../diffpssi_b200/csrc/dps_adjoint.cuh"
+
+extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, double fn, const int* ctrl, int n_obs,
+                             int z_rows, int z_cols, int n_cfg, const uint8_t* step_cfg, int z_per_sim,
+                             const int* slot_vary, int n_rec, const int* rec_chan, long long P, const double* x0,
+                             const double* upar, const double* vpar, const double* zsub, const double* grad_rec,
+                             double* g_x0, double* gslot_all /* [n_gen][DPS_N_SLOTS][P] */) {
+    const int G = n_gen, NS = DPS_N_STATES;
+    const int n_stages = solver == DPS_EULER ? 1 : (solver == DPS_HEUN ? 2 : 4);
+    const long long zb = z_per_sim ? P : 1;
+    double cst[4] = {0, 0, 0, 0}, bst[4] = {0, 0, 0, 0};
+    if (solver == DPS_EULER) { bst[0] = 1.0; }
+    else if (solver == DPS_HEUN) { cst[1] = 1.0; bst[0] = bst[1] = 0.5; }
+    else { cst[1] = 0.5; cst[2] = 0.5; cst[3] = 1.0; bst[0] = 1.0 / 6.0; bst[1] = 1.0 / 3.0; bst[2] = 1.0 / 3.0; bst[3] = 1.0 / 6.0; }
+    std::vector<short> sv(G * DPS_N_SLOTS);
+    for (int i = 0; i < G * DPS_N_SLOTS; ++i) sv[i] = (short)slot_vary[i];
+    (void)n_cfg;
+    for (long long s = 0; s < P; ++s) {
+        const long long zs = z_per_sim ? s : 0;
+        auto z_at = [&](int cfg, int row, int col, double& zr, double& zi) {
+            const double* e = zsub + ((((long long)cfg * z_rows + row) * z_cols + col) * 2) * zb + zs;
+            zr = e[0];
+            zi = e[zb];
+        };
+        auto par_of = [&](int g) { return ParamReader<true>{upar + g * DPS_N_SLOTS, sv.data() + g * DPS_N_SLOTS, vpar, P, s}; };
+        // all stage inputs of one step: X[i][g][k], sd/cd/v per (i, g)
+        auto eval_all = [&](const std::vector<double>& X, int cfg, std::vector<double>& sd, std::vector<double>& cd,
+                            std::vector<double>& vre, std::vector<double>& vim, std::vector<double>& f) {
+            std::vector<double> ire(G), iim(G);
+            for (int g = 0; g < G; ++g) {
+                auto par = par_of(g);
+                sincos(X[g * NS + DPS_X_DELTA], &sd[g], &cd[g]);
+                injection(&X[g * NS], par, sd[g], cd[g], ire[g], iim[g]);
+            }
+            for (int g = 0; g < G; ++g) {
+                auto par = par_of(g);
+                double v_re = 0, v_im = 0;
+                for (int j = 0; j < G; ++j) {
+                    double zr, zi;
+                    z_at(cfg, g, j, zr, zi);
+                    v_re += zr * ire[j] - zi * iim[j];
+                    v_im += zr * iim[j] + zi * ire[j];
+                }
+                vre[g] = v_re;
+                vim[g] = v_im;
+                Algebraics alg;
+                stage_derivatives<true>(&X[g * NS], par, ctrl[g], fn, sd[g], cd[g], v_re, v_im, &f[g * NS], alg);
+            }
+        };
+        // forward pass storing the state at the start of every step (the emulation keeps the whole trajectory)
+        std::vector<std::vector<double>> traj(n_steps, std::vector<double>(G * NS));
+        std::vector<double> x(G * NS), f(G * NS), acc(G * NS), xs(G * NS), sd(G), cd(G), vre(G), vim(G);
+        for (int g = 0; g < G; ++g)
+            for (int k = 0; k < NS; ++k) x[g * NS + k] = x0[((long long)g * NS + k) * P + s];
+        for (int step = 0; step < n_steps; ++step) {
+            traj[step] = x;
+            xs = x;
+            for (int st = 0; st < n_stages; ++st) {
+                eval_all(x, step_cfg[step], sd, cd, vre, vim, f);
+                for (int i = 0; i < G * NS; ++i) {
+                    if (solver == DPS_EULER) x[i] = xs[i] + f[i] * dt;
+                    else if (solver == DPS_HEUN) {
+                        if (st == 0) { acc[i] = f[i]; x[i] = xs[i] + f[i] * dt; }
+                        else x[i] = xs[i] + ((acc[i] + f[i]) * 0.5) * dt;
+                    } else {
+                        if (st == 0) { acc[i] = f[i]; x[i] = xs[i] + (f[i] * dt) * 0.5; }
+                        else if (st == 1) { acc[i] += 2.0 * f[i]; x[i] = xs[i] + (f[i] * dt) * 0.5; }
+                        else if (st == 2) { acc[i] += 2.0 * f[i]; x[i] = xs[i] + f[i] * dt; }
+                        else x[i] = xs[i] + ((acc[i] + f[i]) * dt) / 6.0;
+                    }
+                }
+            }
+        }
+        std::vector<double> lam(G * NS, 0.0), gp(G * DPS_N_SLOTS, 0.0);
+        for (int step = n_steps - 1; step >= 0; --step) {
+            const int cfg = step_cfg[step];
+            for (int c = 0; c < n_rec; ++c)
+                if (rec_chan[3 * c] == DPS_CH_GEN && rec_chan[3 * c + 2] < NS)
+                    lam[rec_chan[3 * c + 1] * NS + rec_chan[3 * c + 2]] += grad_rec[((long long)c * n_steps + step) * P + s];
+            std::vector<std::vector<double>> X(n_stages, std::vector<double>(G * NS)), SD(n_stages, std::vector<double>(G)),
+                CD(n_stages, std::vector<double>(G)), VR(n_stages, std::vector<double>(G)), VI(n_stages, std::vector<double>(G));
+            X[0] = traj[step];
+            for (int i = 0; i < n_stages; ++i) {
+                eval_all(X[i], cfg, SD[i], CD[i], VR[i], VI[i], f);
+                if (i + 1 < n_stages)
+                    for (int k = 0; k < G * NS; ++k) X[i + 1][k] = X[0][k] + cst[i + 1] * (f[k] * dt);
+            }
+            std::vector<double> sum_dx(G * NS, 0.0), dxn(G * NS, 0.0);
+            for (int i = n_stages - 1; i >= 0; --i) {
+                std::vector<double> dk(G * NS), dx(G * NS, 0.0), dvr(G), dvi(G), dsd(G), dcd(G);
+                const double bi = bst[i] * dt, cn = (i + 1 < n_stages) ? cst[i + 1] * dt : 0.0;
+                for (int k = 0; k < G * NS; ++k) dk[k] = bi * lam[k] + cn * dxn[k];
+                for (int g = 0; g < G; ++g) {
+                    auto par = par_of(g);
+                    AlgCot ac = {0, 0, 0, 0, 0, 0, 0};
+                    if (i == n_stages - 1) {
+                        double* av[7] = {&ac.p_e, &ac.i_d, &ac.i_q, &ac.v_re, &ac.v_im, &ac.e_fd, &ac.p_m};
+                        for (int c = 0; c < n_rec; ++c)
+                            if (rec_chan[3 * c] == DPS_CH_GEN && rec_chan[3 * c + 1] == g && rec_chan[3 * c + 2] >= NS)
+                                *av[rec_chan[3 * c + 2] - NS] += grad_rec[((long long)c * n_steps + step) * P + s];
+                    }
+                    stage_vjp<true>(&X[i][g * NS], par, ctrl[g], fn, SD[i][g], CD[i][g], VR[i][g], VI[i][g], &dk[g * NS], ac,
+                                    &dx[g * NS], &gp[g * DPS_N_SLOTS], dsd[g], dcd[g], dvr[g], dvi[g]);
+                }
+                for (int j = 0; j < G; ++j) {
+                    auto par = par_of(j);
+                    double di_re = 0, di_im = 0;
+                    for (int r = 0; r < G; ++r) {
+                        double zr, zi;
+                        z_at(cfg, r, j, zr, zi);
+                        di_re += zr * dvr[r] + zi * dvi[r];
+                        di_im += -zi * dvr[r] + zr * dvi[r];
+                    }
+                    if (i == n_stages - 1) {
+                        for (int c = 0; c < n_rec; ++c) {
+                            const int kind = rec_chan[3 * c];
+                            if (kind == DPS_CH_GEN) continue;
+                            const int r = rec_chan[3 * c + 1];
+                            const double a = grad_rec[((long long)c * n_steps + step) * P + s];
+                            double zr, zi;
+                            z_at(cfg, r, j, zr, zi);
+                            if (kind == DPS_CH_BUS_VRE) { di_re += zr * a; di_im += -zi * a; }
+                            else { di_re += zi * a; di_im += zr * a; }
+                        }
+                    }
+                    injection_vjp(&X[i][j * NS], par, SD[i][j], CD[i][j], di_re, di_im, &dx[j * NS], &gp[j * DPS_N_SLOTS], dsd[j], dcd[j]);
+                    dx[j * NS + DPS_X_DELTA] += dsd[j] * CD[i][j] - dcd[j] * SD[i][j];
+                }
+                dxn = dx;
+                for (int k = 0; k < G * NS; ++k) sum_dx[k] += dx[k];
+            }
+            for (int k = 0; k < G * NS; ++k) lam[k] += sum_dx[k];
+        }
+        for (int g = 0; g < G; ++g) {
+            for (int k = 0; k < NS; ++k) g_x0[((long long)g * NS + k) * P + s] = lam[g * NS + k];
+            for (int k = 0; k < DPS_N_SLOTS; ++k) gslot_all[((long long)g * DPS_N_SLOTS + k) * P + s] = gp[g * DPS_N_SLOTS + k];
+        }
+    }
+    return 0;
+}
