@@ -325,7 +325,7 @@ static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl
         case 6: return launch_bwd_g<6>(p, ctrl, stream);
         case 8: return launch_bwd_g<8>(p, ctrl, stream);
         case 10: return launch_bwd_g<10>(p, ctrl, stream);
-        case 12: return launch_bwd_g<12>(p, ctrl, stream);
+        case 16: return launch_bwd_g<16>(p, ctrl, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -8,20 +8,19 @@ template <int G>
 cudaError_t launch_forward_g(const FwdParams& p, bool ctrl, int pmode, cudaStream_t stream, int* regs);
 
 #define DPS_EXTERN(G) extern template cudaError_t launch_forward_g<G>(const FwdParams&, bool, int, cudaStream_t, int*);
-DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(12)
+DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(16)
 #undef DPS_EXTERN
 
 int fwd_template_g(int n_gen) {
-    static const int sizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 12};
+    static const int sizes[] = {1, 2, 3, 4, 5, 6, 8, 10, 16};
     for (int v : sizes)
         if (n_gen <= v) return v;
     return -1;
 }
 
 void fwd_geometry(int g_template, int* threads, int* sims_per_block) {
-    const int groups = (g_template >= 3) ? 1 : (g_template == 2 ? 2 : 4);
-    *threads = 32 * g_template * groups;
-    *sims_per_block = 32 * groups;
+    *threads = 128;
+    *sims_per_block = 4 * (32 / g_template);
 }
 
 cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, int pmode, cudaStream_t stream, int* regs) {
@@ -34,7 +33,7 @@ cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, int pm
         case 6: return launch_forward_g<6>(p, ctrl, pmode, stream, regs);
         case 8: return launch_forward_g<8>(p, ctrl, pmode, stream, regs);
         case 10: return launch_forward_g<10>(p, ctrl, pmode, stream, regs);
-        case 12: return launch_forward_g<12>(p, ctrl, pmode, stream, regs);
+        case 16: return launch_forward_g<16>(p, ctrl, pmode, stream, regs);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -7,19 +7,22 @@
 // (solvers.py:83,102), the model equations (dps_model.cuh) and the recorder (simulator.py:540-546).
 //
 // Mapping:
-//   * one thread per (trajectory, generator); a warp holds 32 consecutive trajectories of ONE generator, so every
-//     global access is a coalesced 256-byte line and generator-dependent branches / constants are warp-uniform;
-//   * the G warps of one 32-trajectory group exchange their Norton currents through double-buffered shared memory
-//     with a single named barrier (bar.sync id, 32*G) per stage;
-//   * states x, the step-start copy x0 and the stage accumulator stay in registers for all T steps; per step only the
+//   * one thread per (trajectory, generator).  The G generators of one trajectory sit in G adjacent lanes of ONE warp
+//     (a warp holds SPW = 32/G trajectories), so the Norton currents the network solve needs are exchanged with warp
+//     shuffles: no shared-memory round trip, no barrier, and warps never wait for each other -- the SM's schedulers
+//     hide one warp's latency with the others (the earlier block-wide exchange ran 10 warps in lockstep and left the
+//     FP64 pipe idle during every exchange; profiles/ncu_r1d_*);
+//   * states x, the stage input and the stage accumulator stay in registers for all T steps; per step only the
 //     recorder lines go to HBM.
 // Specialisations:
 //   PMODE 1 (fast): the DPS_N_REG_SLOTS leading constants (machine + init-derived set points) of the thread's
 //           (trajectory, generator) are loaded ONCE into registers (per-sim or uniform alike); the remaining controller
-//           constants must be batch-uniform and are warp-broadcast LDS.
+//           constants must be batch-uniform and are read from a bank-conflict-free shared-memory table.
 //   PMODE 2 (generic): any constant may be per-sim; every read goes through the slot table (slow, kept for generality).
 //   ZPS 0: the reduced impedance matrices of all fault configurations are shared by the batch and sit in shared
-//          memory (row read as broadcast LDS.128);  ZPS 1: one matrix per trajectory, row held in registers.
+//          memory, transposed so the lanes of a warp read consecutive addresses;  ZPS 1: one matrix per trajectory,
+//          row held in registers.
+//   SOLVER: the stage sequence is unrolled per scheme, so no register copies are needed between steps.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,58 +33,54 @@ namespace dps {
 
 template <int G>
 struct FwdCfg {
-    // 32-trajectory groups per block: keep blocks at >= 96 threads
-    static constexpr int GROUPS = (G >= 3) ? 1 : (G == 2 ? 2 : 4);
-    static constexpr int THREADS = 32 * G * GROUPS;
-    // resident blocks per SM the register allocator should aim for (register file: 64K x 32 bit per SM, warps are
-    // allocated in groups of 4)
-    static constexpr int MIN_BLOCKS = (THREADS >= 288) ? 1 : (THREADS >= 192 ? 2 : (THREADS >= 128 ? 3 : 4));
+    static constexpr int SPW = 32 / G;             // trajectories per warp
+    static constexpr int WARPS = 4;                // warps are independent; the block size only sets the launch geometry
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int MIN_BLOCKS = 3;           // 12 warps/SM at <= 168 registers
+    static constexpr int UPS = DPS_N_SLOTS + 1;    // row stride of the constant table: odd -> conflict-free per-lane rows
 };
-
-__device__ __forceinline__ void group_barrier(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 template <int G, bool CTRL, int PMODE, int ZPS, int SOLVER>
 __global__ void __launch_bounds__(FwdCfg<G>::THREADS, FwdCfg<G>::MIN_BLOCKS)
 dps_step_kernel(const FwdParams p) {
-    constexpr int GROUPS = FwdCfg<G>::GROUPS;
+    using C = FwdCfg<G>;
+    constexpr int SPW = C::SPW, UPS = C::UPS;
     constexpr int NS = CTRL ? DPS_N_STATES : 6;                                  // live states per generator
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_upar = reinterpret_cast<double*>(smem_raw);                        // [G][DPS_N_SLOTS]
-    double2* s_cur = reinterpret_cast<double2*>(s_upar + G * DPS_N_SLOTS);       // [2][GROUPS][G][32] (re, im)
-    double* s_z = reinterpret_cast<double*>(s_cur + 2 * GROUPS * G * 32);        // ZPS==0: [n_cfg][G][G][2]
-    short* s_vary = reinterpret_cast<short*>(s_z + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0));   // [G][DPS_N_SLOTS]
+    double2* s_z = reinterpret_cast<double2*>(smem_raw);                         // ZPS==0: [n_cfg][col j][row g] (re, im)
+    double* s_upar = reinterpret_cast<double*>(s_z + (ZPS == 0 ? p.n_cfg * G * G : 0));   // [G][UPS]
+    short* s_vary = reinterpret_cast<short*>(s_upar + G * UPS);                  // [G][DPS_N_SLOTS]
 
     const int lane = threadIdx.x & 31;
-    // broadcast from lane 0: tells the compiler the warp index -- and with it the generator index, the controller
-    // flags, the recorder mask and every constant-table address -- is warp-uniform (uniform registers, plain branches)
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int gw = warp % G;                       // generator slot of this warp
-    const int grp = warp / G;                      // trajectory group inside the block
-    const bool gen_live = gw < p.n_gen;            // template G may exceed the real generator count
-    const int g = gen_live ? gw : p.n_gen - 1;
+    const int warp = threadIdx.x >> 5;
+    const int sl = lane / G;                       // trajectory slot inside the warp
+    const int gl = lane - sl * G;                  // generator slot
+    const int base = sl * G;                       // first lane of this trajectory's generator group
+    const bool gen_live = (sl < SPW) && (gl < p.n_gen);     // template G may exceed the real generator count
+    const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
-    const long long sim = ((long long)blockIdx.x * GROUPS + grp) * 32 + lane;
-    const bool live = (sim < P) && gen_live;
+    const long long sim = ((long long)blockIdx.x * C::WARPS + warp) * SPW + sl;
+    const bool live = gen_live && (sim < P);
     const long long s = (sim < P) ? sim : (P - 1);
 
     for (int i = threadIdx.x; i < G * DPS_N_SLOTS; i += blockDim.x) {
-        const bool ok = (i / DPS_N_SLOTS) < p.n_gen;
-        s_upar[i] = ok ? p.upar[i] : 0.0;
+        const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
+        const bool ok = gi < p.n_gen;
+        s_upar[gi * UPS + k] = ok ? p.upar[i] : 0.0;
         if (PMODE == 2) s_vary[i] = ok ? p.slot_vary[i] : (short)-1;
     }
     if (ZPS == 0) {
-        // all configurations of the shared reduced impedance matrix: [cfg][row < G][col < G](re, im)
-        for (int i = threadIdx.x; i < p.n_cfg * G * G * 2; i += blockDim.x) {
-            const int part = i & 1, col = (i >> 1) % G, row = (i >> 1) / G % G, cfg = (i >> 1) / (G * G);
+        for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
+            const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
             const bool ok = row < p.n_gen && col < p.n_gen;
-            s_z[i] = ok ? p.zsub[(((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2 + part] : 0.0;
+            const double* e = p.zsub + (((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2;
+            s_z[i] = ok ? make_double2(e[0], e[1]) : make_double2(0.0, 0.0);
         }
     }
     __syncthreads();
 
-    const double* up = s_upar + g * DPS_N_SLOTS;
+    const double* up = s_upar + g * UPS;
     const int ctrl = CTRL ? p.ctrl[g] : 0;
 
     // ---- parameter access -------------------------------------------------------------------------------------------
@@ -112,18 +111,18 @@ dps_step_kernel(const FwdParams p) {
     double zr[ZPS ? G : 1], zi[ZPS ? G : 1];
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
-    const double2* zrow = nullptr;
+    const double2* zcol = nullptr;                 // ZPS==0: &Zt[cfg][0][gl]; element j at zcol[j*G]
     auto load_z_row = [&](int cfg) {
         if (ZPS) {
-            const double* base = p.zsub + (((long long)cfg * p.z_rows + g) * p.z_cols) * 2 * zb + zs;
+            const double* zbase = p.zsub + (((long long)cfg * p.z_rows + g) * p.z_cols) * 2 * zb + zs;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 const bool ok = j < p.n_gen;
-                zr[ZPS ? j : 0] = ok ? __ldg(base + (long long)(2 * j) * zb) : 0.0;
-                zi[ZPS ? j : 0] = ok ? __ldg(base + (long long)(2 * j + 1) * zb) : 0.0;
+                zr[ZPS ? j : 0] = ok ? __ldg(zbase + (long long)(2 * j) * zb) : 0.0;
+                zi[ZPS ? j : 0] = ok ? __ldg(zbase + (long long)(2 * j + 1) * zb) : 0.0;
             }
         } else {
-            zrow = reinterpret_cast<const double2*>(s_z) + ((long long)cfg * G + gw) * G;
+            zcol = s_z + (long long)cfg * G * G + gl;
         }
     };
 
@@ -135,60 +134,63 @@ dps_step_kernel(const FwdParams p) {
     load_z_row(cfg);
 
     const double dt = p.dt, hdt = 0.5 * p.dt;
-    const int bar_id = grp + 1;
-    double2* cur_grp = s_cur + grp * G * 32 + lane;            // + buf*GROUPS*G*32 + j*32
-    const unsigned rec_mask = p.rec_mask[g];                   // warp-uniform
-    int buf = 0;
+    const unsigned rec_mask = live ? p.rec_mask[g] : 0u;
+    const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
     Algebraics alg;
     int step = p.step_begin;
 
-    // One stage evaluation at state X (reference: the body of one `voltages = matmul(...); for bus: update_voltages;
-    // differential()` pass of solvers.py): Norton currents -> shared memory -> V = Z I -> derivatives f.
+    // One stage evaluation at state X (reference: one `voltages = matmul(...); for bus: update_voltages; differential()`
+    // pass of solvers.py): Norton currents -> warp shuffles -> V = Z I -> derivatives f.
     auto eval = [&](const double* X, double* f, bool last_stage) {
         double sd, cd;
         dps_sincos(X[DPS_X_DELTA], &sd, &cd);
         double i_re, i_im;
         if (PMODE == 1) injection(X, par_fast, sd, cd, i_re, i_im);
         else injection(X, par_gen, sd, cd, i_re, i_im);
-        double2* cb = cur_grp + buf * (GROUPS * G * 32);
-        cb[gw * 32] = gen_live ? make_double2(i_re, i_im) : make_double2(0.0, 0.0);
-        group_barrier(bar_id, 32 * G);
+        if (!gen_live) { i_re = 0.0; i_im = 0.0; }
         // V_g = sum_j Z[g][j] I_j   (solvers.py:83; zero injections at non-generator buses are skipped).
         // Two partial sums per component keep four independent DFMA chains in flight.
         double vra = 0.0, vrb = 0.0, via = 0.0, vib = 0.0;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            const double2 cj = cb[j * 32];
+            const double jr = __shfl_sync(FULL, i_re, base + j);
+            const double ji = __shfl_sync(FULL, i_im, base + j);
             double zre, zim;
             if (ZPS) { zre = zr[ZPS ? j : 0]; zim = zi[ZPS ? j : 0]; }
-            else { const double2 z = zrow[j]; zre = z.x; zim = z.y; }
-            vra = fma(zre, cj.x, vra);
-            vrb = fma(-zim, cj.y, vrb);
-            via = fma(zre, cj.y, via);
-            vib = fma(zim, cj.x, vib);
+            else { const double2 z = zcol[j * G]; zre = z.x; zim = z.y; }
+            vra = fma(zre, jr, vra);
+            vrb = fma(-zim, ji, vrb);
+            via = fma(zre, ji, via);
+            vib = fma(zim, jr, vib);
         }
         const double v_re = vra + vrb, v_im = via + vib;
         if (PMODE == 1) stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         else stage_derivatives<CTRL>(X, par_gen, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
 
-        // extra observed buses (recorded voltages of non-generator buses): last stage only
-        if (last_stage && p.n_obs > p.n_gen && gen_live && sim < P) {
-            for (int r = p.n_gen + g; r < p.n_obs; r += p.n_gen) {
-                const double* base = p.zsub + (((long long)cfg * p.z_rows + r) * p.z_cols) * 2 * zb + zs;
+        // extra observed buses (recorded voltages of non-generator buses): last stage only.  Every lane runs the same
+        // number of iterations because the shuffles need the whole warp.
+        if (last_stage && n_extra_iter > 0) {
+            for (int it = 0; it < n_extra_iter; ++it) {
+                const int r = p.n_gen + it * p.n_gen + g;
+                const bool valid = live && (r < p.n_obs);
+                const int rr = (r < p.n_obs) ? r : p.n_obs - 1;
+                const double* zbase = p.zsub + (((long long)cfg * p.z_rows + rr) * p.z_cols) * 2 * zb + zs;
                 double br = 0.0, bi = 0.0;
                 for (int j = 0; j < p.n_gen; ++j) {
-                    const double zr_ = __ldg(base + (long long)(2 * j) * zb);
-                    const double zi_ = __ldg(base + (long long)(2 * j + 1) * zb);
-                    const double2 cj = cb[j * 32];
-                    br += zr_ * cj.x - zi_ * cj.y;
-                    bi += zr_ * cj.y + zi_ * cj.x;
+                    const double jr = __shfl_sync(FULL, i_re, base + j);
+                    const double ji = __shfl_sync(FULL, i_im, base + j);
+                    const double zr_ = __ldg(zbase + (long long)(2 * j) * zb);
+                    const double zi_ = __ldg(zbase + (long long)(2 * j + 1) * zb);
+                    br += zr_ * jr - zi_ * ji;
+                    bi += zr_ * ji + zi_ * jr;
                 }
-                const int e = r - p.n_gen;
-                if (p.obs_chan[e][0] >= 0) p.rec[((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim] = br;
-                if (p.obs_chan[e][1] >= 0) p.rec[((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim] = bi;
+                if (valid) {
+                    const int e = rr - p.n_gen;
+                    if (p.obs_chan[e][0] >= 0) p.rec[((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim] = br;
+                    if (p.obs_chan[e][1] >= 0) p.rec[((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim] = bi;
+                }
             }
         }
-        buf ^= 1;
     };
 
     for (; step < p.step_end; ++step) {
@@ -239,8 +241,8 @@ dps_step_kernel(const FwdParams p) {
         }
 
         // recorder: post-step states, last-stage algebraics (simulator.py:540-543); rec[chan][step][sim].
-        // The mask is warp-uniform; fields are tested in groups of four so an all-clear group costs one branch.
-        if (rec_mask && live) {
+        // Fields are tested in groups of four so an all-clear group costs one branch.
+        if (rec_mask) {
             const short* ch = p.rec_chan[g];
             double* out = p.rec + (long long)step * P + sim;
             const long long cs = (long long)p.n_steps * P;
@@ -283,13 +285,12 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = sizeof(double) * (G * DPS_N_SLOTS + 2 * C::GROUPS * G * 64 + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0)) +
-                        sizeof(short) * G * DPS_N_SLOTS;
+    const size_t smem = sizeof(double) * (G * C::UPS + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0)) + sizeof(short) * G * DPS_N_SLOTS;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long long sims_per_block = 32LL * C::GROUPS;
+    const long long sims_per_block = (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + sims_per_block - 1) / sims_per_block;
     kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();

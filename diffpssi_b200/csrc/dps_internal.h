@@ -8,7 +8,7 @@
 
 namespace dps {
 
-constexpr int MAX_G = 12;            // generators handled by the register-resident stepper
+constexpr int MAX_G = 16;            // generators handled by the register-resident stepper
 constexpr int MAX_SEG = 48;          // network-configuration change points per launch
 constexpr int MAX_EXTRA_OBS = 24;    // recorded non-generator buses
 
