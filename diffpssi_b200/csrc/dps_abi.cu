@@ -56,6 +56,7 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
     pl->topo.step_cfg = pl->step_cfg.data();
     pl->topo.slot_vary = pl->slot_vary.data();
     pl->topo.rec = pl->rec.data();
+    pl->topo.common_ctrl = nullptr;
 
     for (int k = 0; k < t->n_steps; ++k) {
         if (pl->step_cfg[k] >= t->n_cfg) { set_error("dps_plan_create: step_cfg[%d]=%d >= n_cfg", k, pl->step_cfg[k]); delete pl; return 1; }
@@ -71,6 +72,10 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
         if (v >= t->n_vary) { set_error("dps_plan_create: slot_vary entry %d >= n_vary %d", v, t->n_vary); delete pl; return 1; }
         pl->any_vary |= (v >= 0);
     }
+    pl->cmask = pl->ctrl[0];
+    for (int g = 1; g < t->n_gen; ++g)
+        if (pl->ctrl[g] != pl->ctrl[0]) pl->cmask = -1;
+    if (pl->cmask != 0 && pl->cmask != 7) pl->cmask = -1;
     // fast path: only the DPS_N_REG_SLOTS leading constants may differ between trajectories
     pl->pmode = 1;
     for (int g = 0; g < t->n_gen; ++g)
@@ -79,6 +84,10 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
 
     FwdParams& b = pl->base;
     memset(&b, 0, sizeof(b));
+    if (t->common_ctrl != nullptr && pl->pmode == 1 && pl->cmask == 7) {
+        pl->pmode = 3;
+        for (int k = 0; k < DPS_N_SLOTS; ++k) b.cpar[k] = t->common_ctrl[k];
+    }
     b.n_gen = t->n_gen; b.solver = t->solver; b.n_steps = t->n_steps; b.dt = t->dt; b.fn = t->fn;
     b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.n_cfg = t->n_cfg; b.z_per_sim = t->z_per_sim;
     b.ckpt_stride = t->ckpt_stride;
@@ -131,9 +140,50 @@ int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_pe
     if (g_template) *g_template = plan->g_template;
     if (regs_per_thread) {
         int regs = 0;
-        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->any_ctrl, plan->pmode, 0, &regs);
+        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->cmask, plan->pmode, 0, &regs);
         if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
         *regs_per_thread = regs;
+    }
+    return 0;
+}
+
+// Steps [step_begin, step_end) from state x_in; one launch per MAX_SEG configuration change points (virtually always
+// a single launch).
+static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int step_end, const double* x_in,
+                         const double* upar, const double* vpar, const double* zsub, double* rec, double* x_out,
+                         double* ckpt, void* stream, const char* who) {
+    if (!plan) { set_error("%s: null plan", who); return 1; }
+    if (P < 1) { set_error("%s: P must be >= 1", who); return 1; }
+    if (!x_in || !upar || !zsub) { set_error("%s: null input pointer", who); return 1; }
+    if (plan->topo.n_rec > 0 && !rec) { set_error("%s: recorder channels requested but rec is null", who); return 1; }
+    if (plan->any_vary && !vpar) { set_error("%s: per-sim constants requested but vpar is null", who); return 1; }
+    if (plan->topo.ckpt_stride > 0 && !ckpt) { set_error("%s: checkpoints requested but ckpt is null", who); return 1; }
+    if (step_begin < 0 || step_end > plan->topo.n_steps || step_begin > step_end) { set_error("%s: bad step range [%d, %d)", who, step_begin, step_end); return 1; }
+    if (step_begin == step_end) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_seg = (int)plan->seg_step.size();
+    // first segment that covers step_begin
+    int seg0 = 0;
+    while (seg0 + 1 < n_seg && plan->seg_step[seg0 + 1] <= step_begin) ++seg0;
+    int begin = step_begin;
+    while (begin < step_end) {
+        int seg1 = seg0 + 1;
+        while (seg1 < n_seg && seg1 - seg0 < MAX_SEG && plan->seg_step[seg1] < step_end) ++seg1;
+        const int end = (seg1 < n_seg && plan->seg_step[seg1] < step_end) ? plan->seg_step[seg1] : step_end;
+        FwdParams p = plan->base;
+        p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub;
+        p.rec = rec; p.ckpt = ckpt;
+        p.step_begin = begin;
+        p.step_end = end;
+        p.n_seg = seg1 - seg0;
+        for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
+        if (end < step_end && !x_out) { set_error("%s: more than %d configuration changes need x_final as carry buffer", who, MAX_SEG); return 1; }
+        p.x_final = x_out;
+        cudaError_t e = launch_forward(p, plan->g_template, plan->cmask, plan->pmode, st, nullptr);
+        if (e != cudaSuccess) { set_error("%s: launch failed: %s", who, cudaGetErrorString(e)); return 3; }
+        x_in = x_out;
+        begin = end;
+        seg0 = seg1;
     }
     return 0;
 }
@@ -141,36 +191,13 @@ int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_pe
 int dps_forward(const dps_plan* plan, int64_t P, const double* x0, const double* upar, const double* vpar,
                 const double* zsub, double* rec, double* x_final, double* ckpt, void* stream) {
     if (!plan) { set_error("dps_forward: null plan"); return 1; }
-    if (P < 1) { set_error("dps_forward: P must be >= 1"); return 1; }
-    if (!x0 || !upar || !zsub) { set_error("dps_forward: null input pointer"); return 1; }
-    if (plan->topo.n_rec > 0 && !rec) { set_error("dps_forward: recorder channels requested but rec is null"); return 1; }
-    if (plan->any_vary && !vpar) { set_error("dps_forward: per-sim constants requested but vpar is null"); return 1; }
-    if (plan->topo.ckpt_stride > 0 && !ckpt) { set_error("dps_forward: checkpoints requested but ckpt is null"); return 1; }
-    if (plan->topo.n_steps == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+    return forward_range(plan, P, 0, plan->topo.n_steps, x0, upar, vpar, zsub, rec, x_final, ckpt, stream, "dps_forward");
+}
 
-    // one launch per MAX_SEG configuration change points (virtually always a single launch)
-    const int n_seg = (int)plan->seg_step.size();
-    const double* x_in = x0;
-    int seg0 = 0;
-    while (seg0 < n_seg) {
-        const int seg1 = (seg0 + MAX_SEG < n_seg) ? seg0 + MAX_SEG : n_seg;
-        FwdParams p = plan->base;
-        p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub;
-        p.rec = rec; p.ckpt = ckpt;
-        p.step_begin = plan->seg_step[seg0];
-        p.step_end = (seg1 < n_seg) ? plan->seg_step[seg1] : plan->topo.n_steps;
-        p.n_seg = seg1 - seg0;
-        for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
-        const bool last = (seg1 == n_seg);
-        if (!last && !x_final) { set_error("dps_forward: more than %d configuration changes need x_final as carry buffer", MAX_SEG); return 1; }
-        p.x_final = x_final;
-        cudaError_t e = launch_forward(p, plan->g_template, plan->any_ctrl, plan->pmode, st, nullptr);
-        if (e != cudaSuccess) { set_error("dps_forward: launch failed: %s", cudaGetErrorString(e)); return 3; }
-        x_in = x_final;
-        seg0 = seg1;
-    }
-    return 0;
+int dps_forward_range(const dps_plan* plan, int64_t P, int32_t step_begin, int32_t step_end, const double* x_in,
+                      const double* upar, const double* vpar, const double* zsub, double* rec, double* x_out,
+                      double* ckpt, void* stream) {
+    return forward_range(plan, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt, stream, "dps_forward_range");
 }
 
 int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const double* z_im, const double* yd_re,

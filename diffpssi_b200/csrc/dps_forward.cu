@@ -5,9 +5,9 @@
 namespace dps {
 
 template <int G>
-cudaError_t launch_forward_g(const FwdParams& p, bool ctrl, int pmode, cudaStream_t stream, int* regs);
+cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs);
 
-#define DPS_EXTERN(G) extern template cudaError_t launch_forward_g<G>(const FwdParams&, bool, int, cudaStream_t, int*);
+#define DPS_EXTERN(G) extern template cudaError_t launch_forward_g<G>(const FwdParams&, int, int, cudaStream_t, int*);
 DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(16)
 #undef DPS_EXTERN
 
@@ -23,17 +23,17 @@ void fwd_geometry(int g_template, int* threads, int* sims_per_block) {
     *sims_per_block = 4 * (32 / g_template);
 }
 
-cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, int pmode, cudaStream_t stream, int* regs) {
+cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream, int* regs) {
     switch (g_template) {
-        case 1: return launch_forward_g<1>(p, ctrl, pmode, stream, regs);
-        case 2: return launch_forward_g<2>(p, ctrl, pmode, stream, regs);
-        case 3: return launch_forward_g<3>(p, ctrl, pmode, stream, regs);
-        case 4: return launch_forward_g<4>(p, ctrl, pmode, stream, regs);
-        case 5: return launch_forward_g<5>(p, ctrl, pmode, stream, regs);
-        case 6: return launch_forward_g<6>(p, ctrl, pmode, stream, regs);
-        case 8: return launch_forward_g<8>(p, ctrl, pmode, stream, regs);
-        case 10: return launch_forward_g<10>(p, ctrl, pmode, stream, regs);
-        case 16: return launch_forward_g<16>(p, ctrl, pmode, stream, regs);
+        case 1: return launch_forward_g<1>(p, cmask, pmode, stream, regs);
+        case 2: return launch_forward_g<2>(p, cmask, pmode, stream, regs);
+        case 3: return launch_forward_g<3>(p, cmask, pmode, stream, regs);
+        case 4: return launch_forward_g<4>(p, cmask, pmode, stream, regs);
+        case 5: return launch_forward_g<5>(p, cmask, pmode, stream, regs);
+        case 6: return launch_forward_g<6>(p, cmask, pmode, stream, regs);
+        case 8: return launch_forward_g<8>(p, cmask, pmode, stream, regs);
+        case 10: return launch_forward_g<10>(p, cmask, pmode, stream, regs);
+        case 16: return launch_forward_g<16>(p, cmask, pmode, stream, regs);
         default: return cudaErrorInvalidValue;
     }
 }

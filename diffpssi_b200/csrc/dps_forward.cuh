@@ -18,6 +18,8 @@
 //   PMODE 1 (fast): the DPS_N_REG_SLOTS leading constants (machine + init-derived set points) of the thread's
 //           (trajectory, generator) are loaded ONCE into registers (per-sim or uniform alike); the remaining controller
 //           constants must be batch-uniform and are read from a bank-conflict-free shared-memory table.
+//   PMODE 3 (fastest): PMODE 1 plus: every generator has all three controllers with constants that are identical between
+//           generators; they sit in the kernel parameter block and fold into the instructions as constant-bank operands.
 //   PMODE 2 (generic): any constant may be per-sim; every read goes through the slot table (slow, kept for generality).
 //   ZPS 0: the reduced impedance matrices of all fault configurations are shared by the batch and sit in shared
 //          memory, transposed so the lanes of a warp read consecutive addresses;  ZPS 1: one matrix per trajectory,
@@ -26,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "dps_internal.h"
 #include "dps_model.cuh"
 
@@ -36,27 +39,31 @@ struct FwdCfg {
     static constexpr int SPW = 32 / G;             // trajectories per warp
     static constexpr int WARPS = 4;                // warps are independent; the block size only sets the launch geometry
     static constexpr int THREADS = 32 * WARPS;
-    static constexpr int MIN_BLOCKS = 3;           // 12 warps/SM at <= 168 registers
+#ifndef DPS_MIN_BLOCKS
+#define DPS_MIN_BLOCKS 3
+#endif
+    static constexpr int MIN_BLOCKS = DPS_MIN_BLOCKS;   // 3 -> 12 warps/SM at <= 168 registers
     static constexpr int UPS = DPS_N_SLOTS + 1;    // row stride of the constant table: odd -> conflict-free per-lane rows
 };
 
-template <int G, bool CTRL, int PMODE, int ZPS, int SOLVER>
+template <int G, int CM, int PMODE, int ZPS, int SOLVER>
 __global__ void __launch_bounds__(FwdCfg<G>::THREADS, FwdCfg<G>::MIN_BLOCKS)
 dps_step_kernel(const FwdParams p) {
     using C = FwdCfg<G>;
     constexpr int SPW = C::SPW, UPS = C::UPS;
-    constexpr int NS = CTRL ? DPS_N_STATES : 6;                                  // live states per generator
-    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool CTRL = (CM != 0);                 // CM: -1 = per-generator controller flags, else the common flag set
+    constexpr int NS = CTRL ? DPS_N_STATES : 6;      // live states per generator
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* s_z = reinterpret_cast<double2*>(smem_raw);                         // ZPS==0: [n_cfg][col j][row g] (re, im)
-    double* s_upar = reinterpret_cast<double*>(s_z + (ZPS == 0 ? p.n_cfg * G * G : 0));   // [G][UPS]
+    double2* s_cur = s_z + (ZPS == 0 ? p.n_cfg * G * G : 0);                     // [WARPS][2][32] current exchange lines
+    double* s_upar = reinterpret_cast<double*>(s_cur + C::WARPS * 64);           // [G][UPS]
     short* s_vary = reinterpret_cast<short*>(s_upar + G * UPS);                  // [G][DPS_N_SLOTS]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sl = lane / G;                       // trajectory slot inside the warp
     const int gl = lane - sl * G;                  // generator slot
-    const int base = sl * G;                       // first lane of this trajectory's generator group
+    const int base = ((sl < SPW) ? sl : SPW - 1) * G;   // first lane of this trajectory's generator group
     const bool gen_live = (sl < SPW) && (gl < p.n_gen);     // template G may exceed the real generator count
     const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
@@ -81,11 +88,11 @@ dps_step_kernel(const FwdParams p) {
     __syncthreads();
 
     const double* up = s_upar + g * UPS;
-    const int ctrl = CTRL ? p.ctrl[g] : 0;
+    const int ctrl = (CM >= 0) ? CM : p.ctrl[g];
 
     // ---- parameter access -------------------------------------------------------------------------------------------
     double pm[DPS_N_REG_SLOTS];
-    if (PMODE == 1) {
+    if (PMODE == 1 || PMODE == 3) {
 #pragma unroll
         for (int k = 0; k < DPS_N_REG_SLOTS; ++k) {
             const int vi = p.slot_vary[g * DPS_N_SLOTS + k];
@@ -93,6 +100,7 @@ dps_step_kernel(const FwdParams p) {
         }
     }
     ParamRegs par_fast{pm, up};
+    ParamConst par_const{pm, p.cpar};
     ParamReader<true> par_gen;
     par_gen.up = up;
     par_gen.sv = s_vary + g * DPS_N_SLOTS;
@@ -136,25 +144,37 @@ dps_step_kernel(const FwdParams p) {
     const double dt = p.dt, hdt = 0.5 * p.dt;
     const unsigned rec_mask = live ? p.rec_mask[g] : 0u;
     const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
-    Algebraics alg;
     int step = p.step_begin;
+    int buf = 0;
+    // dummy lanes of a partially filled warp read the last real group
+    double2* cur_w = s_cur + warp * 64;
 
     // One stage evaluation at state X (reference: one `voltages = matmul(...); for bus: update_voltages; differential()`
     // pass of solvers.py): Norton currents -> warp shuffles -> V = Z I -> derivatives f.
     auto eval = [&](const double* X, double* f, bool last_stage) {
+        Algebraics alg;
         double sd, cd;
         dps_sincos(X[DPS_X_DELTA], &sd, &cd);
         double i_re, i_im;
-        if (PMODE == 1) injection(X, par_fast, sd, cd, i_re, i_im);
+        if (PMODE == 3) injection(X, par_const, sd, cd, i_re, i_im);
+        else if (PMODE == 1) injection(X, par_fast, sd, cd, i_re, i_im);
         else injection(X, par_gen, sd, cd, i_re, i_im);
         if (!gen_live) { i_re = 0.0; i_im = 0.0; }
+        // exchange inside the warp through its private, double-buffered shared-memory line: one STS.128, then every
+        // lane reads the G currents of its own trajectory as broadcast LDS.128 (a quarter of the wavefronts the
+        // equivalent 4*G 32-bit shuffles cost); __syncwarp orders the store against the loads.
+        double2* cw = cur_w + buf * 32;
+        cw[lane] = make_double2(i_re, i_im);
+        __syncwarp();
+        buf ^= 1;
+        const double2* cgrp = cw + base;
         // V_g = sum_j Z[g][j] I_j   (solvers.py:83; zero injections at non-generator buses are skipped).
         // Two partial sums per component keep four independent DFMA chains in flight.
         double vra = 0.0, vrb = 0.0, via = 0.0, vib = 0.0;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            const double jr = __shfl_sync(FULL, i_re, base + j);
-            const double ji = __shfl_sync(FULL, i_im, base + j);
+            const double2 cj = cgrp[j];
+            const double jr = cj.x, ji = cj.y;
             double zre, zim;
             if (ZPS) { zre = zr[ZPS ? j : 0]; zim = zi[ZPS ? j : 0]; }
             else { const double2 z = zcol[j * G]; zre = z.x; zim = z.y; }
@@ -164,9 +184,20 @@ dps_step_kernel(const FwdParams p) {
             vib = fma(zim, jr, vib);
         }
         const double v_re = vra + vrb, v_im = via + vib;
-        if (PMODE == 1) stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        if (PMODE == 3) stage_derivatives<CTRL>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        else if (PMODE == 1) stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         else stage_derivatives<CTRL>(X, par_gen, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
 
+        // recorded algebraics hold the values of the LAST stage evaluation of the step (simulator.py:540-543)
+        if (last_stage && (rec_mask >> DPS_N_STATES)) {
+            const short* ch = p.rec_chan[g];
+            double* out = p.rec + (long long)step * P + sim;
+            const long long cs = (long long)p.n_steps * P;
+            const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                if (rec_mask & (1u << (DPS_N_STATES + k))) out[ch[DPS_N_STATES + k] * cs] = av[k];
+        }
         // extra observed buses (recorded voltages of non-generator buses): last stage only.  Every lane runs the same
         // number of iterations because the shuffles need the whole warp.
         if (last_stage && n_extra_iter > 0) {
@@ -177,8 +208,7 @@ dps_step_kernel(const FwdParams p) {
                 const double* zbase = p.zsub + (((long long)cfg * p.z_rows + rr) * p.z_cols) * 2 * zb + zs;
                 double br = 0.0, bi = 0.0;
                 for (int j = 0; j < p.n_gen; ++j) {
-                    const double jr = __shfl_sync(FULL, i_re, base + j);
-                    const double ji = __shfl_sync(FULL, i_im, base + j);
+                    const double jr = cgrp[j].x, ji = cgrp[j].y;
                     const double zr_ = __ldg(zbase + (long long)(2 * j) * zb);
                     const double zi_ = __ldg(zbase + (long long)(2 * j + 1) * zb);
                     br += zr_ * jr - zi_ * ji;
@@ -216,14 +246,15 @@ dps_step_kernel(const FwdParams p) {
 #pragma unroll
             for (int k = 0; k < NS; ++k) x[k] = x[k] + f[k] * dt;
         } else if (SOLVER == DPS_HEUN) {              // solvers.py:83-114: x0 + ((f0 + f1)/2)*dt
-            double xt[NS], acc[NS];
+            // Evaluated as (x0 + f0*dt/2) + f1*dt/2: x0 and f0 die after the first stage, which frees 26 registers
+            // for the price of one extra rounding per state and step (~1e-16 relative; parity budget 1e-9).
+            double xt[NS];
             eval(x, f, false);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; xt[k] = x[k] + f[k] * dt; }
+            for (int k = 0; k < NS; ++k) { xt[k] = fma(f[k], dt, x[k]); x[k] = fma(f[k], hdt, x[k]); }
             eval(xt, f, true);
-            // ((f0+f1)/2)*dt == (f0+f1)*(dt/2) bit for bit: halving is exact
 #pragma unroll
-            for (int k = 0; k < NS; ++k) x[k] = x[k] + (acc[k] + f[k]) * hdt;
+            for (int k = 0; k < NS; ++k) x[k] = fma(f[k], hdt, x[k]);
         } else {                                      // solvers.py:150-214
             double xt[NS], acc[NS];
             eval(x, f, false);
@@ -240,23 +271,18 @@ dps_step_kernel(const FwdParams p) {
             for (int k = 0; k < NS; ++k) x[k] = x[k] + ((acc[k] + f[k]) * dt) / 6.0;
         }
 
-        // recorder: post-step states, last-stage algebraics (simulator.py:540-543); rec[chan][step][sim].
-        // Fields are tested in groups of four so an all-clear group costs one branch.
-        if (rec_mask) {
+        // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim].  Fields are tested in groups of
+        // four so an all-clear group costs one branch.  (Algebraics were stored by the last stage evaluation.)
+        if (rec_mask & 0x1FFFu) {
             const short* ch = p.rec_chan[g];
             double* out = p.rec + (long long)step * P + sim;
             const long long cs = (long long)p.n_steps * P;
-            const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
 #pragma unroll
-            for (int grp4 = 0; grp4 < DPS_N_FIELDS; grp4 += 4) {
-                if (rec_mask & (0xFu << grp4)) {
+            for (int grp4 = 0; grp4 < 16; grp4 += 4) {
+                if (rec_mask & (0xFu << grp4) & 0x1FFFu) {
 #pragma unroll
-                    for (int k = grp4; k < grp4 + 4; ++k) {
-                        if (rec_mask & (1u << k)) {
-                            const double v = (k < NS) ? x[k < NS ? k : 0] : (k < DPS_N_STATES ? 0.0 : av[k >= DPS_N_STATES ? k - DPS_N_STATES : 0]);
-                            out[ch[k] * cs] = v;
-                        }
-                    }
+                    for (int k = grp4; k < grp4 + 4 && k < DPS_N_STATES; ++k)
+                        if (rec_mask & (1u << k)) out[ch[k] * cs] = (k < NS) ? x[k < NS ? k : 0] : 0.0;
                 }
             }
         }
@@ -274,10 +300,10 @@ dps_step_kernel(const FwdParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // launch helpers (one instantiation set per G, see dps_forward_inst.cu)
 // ---------------------------------------------------------------------------------------------------------
-template <int G, bool CTRL, int PMODE, int ZPS, int SOLVER>
+template <int G, int CM, int PMODE, int ZPS, int SOLVER>
 static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs) {
     using C = FwdCfg<G>;
-    auto kern = dps_step_kernel<G, CTRL, PMODE, ZPS, SOLVER>;
+    auto kern = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER>;
     if (regs) {
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, kern);
@@ -285,7 +311,8 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = sizeof(double) * (G * C::UPS + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0)) + sizeof(short) * G * DPS_N_SLOTS;
+    const size_t smem = sizeof(double) * (G * C::UPS + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0)) +
+                        sizeof(short) * G * DPS_N_SLOTS + sizeof(double2) * C::WARPS * 64;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -297,16 +324,19 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
 }
 
 template <int G>
-cudaError_t launch_forward_g(const FwdParams& p, bool ctrl, int pmode, cudaStream_t stream, int* regs) {
-    const int zps = p.z_per_sim ? 1 : 0;
+cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs) {
+    // DPS_FORCE_ZREG=1 (experiments): keep the row of a batch-shared Z in registers instead of shared memory
+    static const bool force_zreg = (getenv("DPS_FORCE_ZREG") != nullptr);
+    const int zps = (p.z_per_sim || force_zreg) ? 1 : 0;
 #define DPS_CASE(C, M, Z)                                                                          \
-    if (ctrl == C && pmode == M && zps == Z) {                                                     \
+    if (cmask == C && pmode == M && zps == Z) {                                                     \
         if (p.solver == DPS_EULER) return launch_one<G, C, M, Z, DPS_EULER>(p, stream, regs);      \
         if (p.solver == DPS_HEUN) return launch_one<G, C, M, Z, DPS_HEUN>(p, stream, regs);        \
         return launch_one<G, C, M, Z, DPS_RK4>(p, stream, regs);                                   \
     }
-    DPS_CASE(false, 1, 0) DPS_CASE(false, 1, 1) DPS_CASE(false, 2, 0) DPS_CASE(false, 2, 1)
-    DPS_CASE(true, 1, 0) DPS_CASE(true, 1, 1) DPS_CASE(true, 2, 0) DPS_CASE(true, 2, 1)
+    DPS_CASE(0, 1, 0) DPS_CASE(0, 1, 1) DPS_CASE(0, 2, 0) DPS_CASE(0, 2, 1)
+    DPS_CASE(7, 1, 0) DPS_CASE(7, 1, 1) DPS_CASE(7, 2, 0) DPS_CASE(7, 2, 1) DPS_CASE(7, 3, 0) DPS_CASE(7, 3, 1)
+    DPS_CASE(-1, 1, 0) DPS_CASE(-1, 1, 1) DPS_CASE(-1, 2, 0) DPS_CASE(-1, 2, 1)
 #undef DPS_CASE
     return cudaErrorInvalidValue;
 }

@@ -32,12 +32,13 @@ struct FwdParams {
     short rec_chan[MAX_G][DPS_N_FIELDS];    // channel index of field k
     short obs_chan[MAX_EXTRA_OBS][2];       // channel of (re, im) of extra observed row e, or -1
     short slot_vary[MAX_G * DPS_N_SLOTS];   // row of vpar or -1
+    double cpar[DPS_N_SLOTS];               // PMODE 3: controller constants common to all generators
 };
 
 int fwd_template_g(int n_gen);
 void fwd_geometry(int g_template, int* threads, int* sims_per_block);
 #ifdef __CUDACC__
-cudaError_t launch_forward(const FwdParams& p, int g_template, bool ctrl, int pmode, cudaStream_t stream,
+cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream,
                            int* regs_query);
 #endif
 

@@ -118,6 +118,17 @@ struct ParamRegs {
     }
 };
 
+// Fastest reader (PMODE 3): as ParamRegs, but the controller constants are identical for every generator and every
+// trajectory, live in the kernel's parameter block (constant bank) and fold into the FP64 instructions as c[0][off]
+// operands -- no load instruction, no shared-memory wavefront.
+struct ParamConst {
+    const double* pm;        // registers, [DPS_N_REG_SLOTS]
+    const double* cp;        // kernel parameter block, [DPS_N_SLOTS]
+    __device__ __forceinline__ double operator()(int slot) const {
+        return (slot < DPS_N_REG_SLOTS) ? pm[slot] : cp[slot];
+    }
+};
+
 struct Algebraics {            // values the reference keeps on the machine object after a stage
     double p_e, i_d, i_q, v_re, v_im, e_fd, p_m;
 };

@@ -12,6 +12,7 @@ struct dps_plan {
     std::vector<int> seg_step, seg_cfg;   // configuration change points
     int g_template;
     bool any_ctrl, any_vary;
+    int cmask;                            // common controller flag set of all generators (0 or 7), or -1 if mixed
     int pmode;                            // 1 = machine constants in registers, 2 = generic slot table
     dps::FwdParams base;                       // everything that does not depend on the call
 };

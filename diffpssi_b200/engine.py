@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdps_b200.so')
+LIB_PATH = os.environ.get('DPS_B200_LIB') or os.path.join(_HERE, 'libdps_b200.so')   # override: kernel A/B experiments
 
 ABI_VERSION = 1
 N_STATES = 13
@@ -22,7 +22,7 @@ MAX_CFG = 16
 MAX_FAULT = 8
 
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes',
-           'dps_network_reduce', 'dps_forward', 'dps_backward', 'dps_fp64_peak_probe', 'dps_plan_info',
+           'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_plan_info',
            'dps_last_error', 'dps_abi_version')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
@@ -49,6 +49,7 @@ class Topology(ctypes.Structure):
         ('n_vary', ctypes.c_int32), ('n_rec', ctypes.c_int32),
         ('rec', ctypes.POINTER(Channel)),
         ('ckpt_stride', ctypes.c_int32),
+        ('common_ctrl', ctypes.POINTER(ctypes.c_double)),
     ]
 
 
@@ -78,6 +79,7 @@ def load_library(path=None):
     lib.dps_network_reduce.argtypes = [i64, i32, vp, vp, vp, vp, i32, ctypes.POINTER(i32), i32, ctypes.POINTER(i32),
                                        i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dbl, vp, vp]
     lib.dps_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dps_forward_range.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dps_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint8), vp, vp, vp,
                                  ctypes.c_size_t, vp]
     lib.dps_fp64_peak_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
@@ -129,7 +131,11 @@ class Plan(object):
         t = Topology(ABI_VERSION, G, topo['solver'], T, topo['dt'], topo['fn'], self._ctrl,
                      topo['n_obs'], topo['z_rows'], topo['z_cols'], topo['n_cfg'], self._step_cfg,
                      topo['z_per_sim'], self._slot_vary, topo['n_vary'], len(chans), self._rec,
-                     topo.get('ckpt_stride', 0))
+                     topo.get('ckpt_stride', 0), None)
+        cc = topo.get('common_ctrl')
+        if cc is not None:
+            self._cc = (ctypes.c_double * N_SLOTS)(*cc)
+            t.common_ctrl = self._cc
         self._t = t
         h = ctypes.c_void_p()
         _check(self.lib, self.lib.dps_plan_create(ctypes.byref(t), ctypes.byref(h)), 'dps_plan_create')
@@ -157,6 +163,12 @@ class Plan(object):
         require_cuda()
         _check(self.lib, self.lib.dps_forward(self.handle, P, _ptr(x0), _ptr(upar), _ptr(vpar), _ptr(zsub),
                                               _ptr(rec), _ptr(x_final), _ptr(ckpt), _stream()), 'dps_forward')
+
+    def forward_range(self, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt=None):
+        require_cuda()
+        _check(self.lib, self.lib.dps_forward_range(self.handle, P, step_begin, step_end, _ptr(x_in), _ptr(upar),
+                                                    _ptr(vpar), _ptr(zsub), _ptr(rec), _ptr(x_out), _ptr(ckpt),
+                                                    _stream()), 'dps_forward_range')
 
 
 def network_reduce(z_re, z_im, yd_re, yd_im, obs_bus, gen_bus, cfg_sets, y_fault, zsub):

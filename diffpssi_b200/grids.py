@@ -69,7 +69,9 @@ def ieee39():
                                [['G%d' % (i + 1), 'B%d' % b, sn, 345, p, v, h, 0, xd, xq, xdt, xqt, xst, xst, 8.0, 0.4, 0.03, 0.05]
                                 for i, (b, sn, p, v, h, xd, xq, xdt, xqt, xst) in enumerate(gens)]},
         'gov': {'TGOV1': [['name', 'gen', 'R', 'D_t', 'V_min', 'V_max', 'T_1', 'T_2', 'T_3']] +
-                          [['GOV%d' % (i + 1), 'G%d' % (i + 1), 0.05, 0.02, 0 if i < 9 else -1, 1, 0.5, 1, 2] for i in range(10)]},
+                          # V_min = -1 everywhere: the net-import equivalent G10 runs at p_m < 0, and identical
+                          # controller settings on all machines let the stepper use its constant-bank path
+                          [['GOV%d' % (i + 1), 'G%d' % (i + 1), 0.05, 0.02, -1, 1, 0.5, 1, 2] for i in range(10)]},
         'avr': {'SEXS': [['name', 'gen', 'K', 'T_a', 'T_b', 'T_e', 'E_min', 'E_max']] +
                          [['AVR%d' % (i + 1), 'G%d' % (i + 1), 100, 2.0, 10.0, 0.1, -5, 5] for i in range(10)]},
         'pss': {'STAB1': [['name', 'gen', 'K', 'T', 'T_1', 'T_2', 'T_3', 'T_4', 'H_lim']] +

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from . import engine
-from .prologue import SLOTS, SLOT_INDEX, N_SLOTS, CTRL_AVR, CTRL_GOV, CTRL_PSS
+from .prologue import SLOTS, SLOT_INDEX, N_SLOTS, N_REG_SLOTS, CTRL_AVR, CTRL_GOV, CTRL_PSS
 
 F64 = torch.float64
 FIELD_VRE, FIELD_VIM = 16, 17
@@ -82,6 +82,22 @@ def pack_slots(init, P, device):
     upar = torch.stack(urows, dim=0).contiguous()
     vpar = torch.stack(vrows, dim=0).contiguous() if vrows else None
     return upar, vpar, slot_vary
+
+
+def common_controller_constants(init, upar, slot_vary):
+    """Host list [N_SLOTS] of the controller constants when every generator has all three controllers and their
+    (batch-uniform) constants are identical between generators -- the stepper then takes them as constant-bank operands
+    (``dps_topology.common_ctrl``).  None otherwise.  One small device->host read per run()."""
+    if any(f != (CTRL_AVR | CTRL_GOV | CTRL_PSS) for f in init.ctrl):
+        return None
+    G = len(init.ctrl)
+    if any(slot_vary[g * N_SLOTS + k] >= 0 for g in range(G) for k in range(N_REG_SLOTS, N_SLOTS)):
+        return None
+    host = upar.detach().cpu()
+    tail = host[:, N_REG_SLOTS:]
+    if not bool((tail == tail[:1]).all()):
+        return None
+    return [float(v) for v in host[0]]
 
 
 def observed_rows(init, channel_keys):

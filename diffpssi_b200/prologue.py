@@ -390,3 +390,66 @@ def initial_injections(res):
         cur.append((i_d + i_q) * sl['snr'])
     B = max(c.shape[0] for c in cur)
     return torch.cat([c.expand(B, 1) for c in cur], dim=1)
+
+
+# ==================================================================================================
+# parameter events
+# ==================================================================================================
+INIT_DERIVED = ('pm0', 'efd0', 'a_vset', 'a_bias', 'g_pref')
+
+
+def refresh_loop_slots(sim, init, device):
+    """Constant slots after a ParamEvent changed a model attribute mid-run (static_models.py:82-95, applied at
+    simulator.py:533-534).  The reference only ``setattr``s: nothing is re-initialised, so the values initialize() left
+    behind (p_m / e_fd of uncontrolled machines, v_setpoint, bias, p_ref) and Z stay as they are; every other constant
+    is re-derived from the current attributes with the same expressions as in :func:`initialize`."""
+    col = _Cols(sim.parallel_sims, device)
+    out = []
+    for g, old in zip(init.gens, init.slots):
+        c = {k: col(getattr(g, k), C128) for k in ('s_n', 'h', 'd', 'x_d', 'x_q', 'x_d_t', 'x_q_t', 'x_d_st', 'x_q_st',
+                                                   't_d0_t', 't_q0_t', 't_d0_st', 't_q0_st')}
+        sl = {
+            'inv_2h': _real(1 / (2 * c['h'])), 'd': _real(c['d']),
+            'inv_td0t': _real(1 / c['t_d0_t']), 'xd_xdt': _real(c['x_d'] - c['x_d_t']),
+            'inv_tq0t': _real(1 / c['t_q0_t']), 'xq_xqt': _real(c['x_q'] - c['x_q_t']),
+            'inv_td0st': _real(1 / c['t_d0_st']), 'xdt_xdst': _real(c['x_d_t'] - c['x_d_st']),
+            'inv_tq0st': _real(1 / c['t_q0_st']), 'xqt_xqst': _real(c['x_q_t'] - c['x_q_st']),
+            'inv_xdst': _real(1 / c['x_d_st']), 'inv_xqst': _real(1 / c['x_q_st']),
+            'snr': _real(c['s_n'] / g.s_n_sys),
+        }
+        if g.exciter:
+            ll, pt = g.exciter.lead_lag, g.exciter.pt1_lim
+            r = col(ll.t_1, None) / col(ll.t_2, None)
+            sl.update({'a_r': _real(r), 'a_omr': _real(1 - r), 'a_inv_tb': _real(1 / col(ll.t_2, None)),
+                       'a_inv_te': _real(1 / col(pt.t_pt1, None)), 'a_k': _real(col(pt.gain_pt1, None)),
+                       'a_emin': _real(col(pt.lim_min, None)), 'a_emax': _real(col(pt.lim_max, None))})
+        if g.governor:
+            pt, ll = g.governor.pt1_lim, g.governor.lead_lag
+            r = col(ll.t_1, None) / col(ll.t_2, None)
+            sl.update({'g_inv_t1': _real(1 / col(pt.t_pt1, None)), 'g_gain': _real(col(pt.gain_pt1, None)),
+                       'g_vmin': _real(col(pt.lim_min, None)), 'g_vmax': _real(col(pt.lim_max, None)),
+                       'g_r': _real(r), 'g_omr': _real(1 - r), 'g_inv_t3': _real(1 / col(ll.t_2, None)),
+                       'g_dt': _real(col(g.governor.d_t, None))})
+        if g.stabilizer:
+            st = g.stabilizer
+            r1 = col(st.lead_lag1.t_1, None) / col(st.lead_lag1.t_2, None)
+            r2 = col(st.lead_lag2.t_1, None) / col(st.lead_lag2.t_2, None)
+            sl.update({'s_inv_tw': _real(1 / col(st.washout.t_w, None)), 's_kw': _real(col(st.washout.k_w, None)),
+                       's_r1': _real(r1), 's_omr1': _real(1 - r1), 's_inv_t3': _real(1 / col(st.lead_lag1.t_2, None)),
+                       's_r2': _real(r2), 's_omr2': _real(1 - r2), 's_inv_t4': _real(1 / col(st.lead_lag2.t_2, None)),
+                       's_hlim': _real(col(st.limiter.limit, None))})
+        for k in INIT_DERIVED:
+            if k in old:
+                sl[k] = old[k]
+        # the reference keeps p_m / e_fd as plain attributes of the machine: a ParamEvent may overwrite them too
+        if not g.governor:
+            sl['pm0'] = _real(col(g.p_m, C128))
+        if not g.exciter:
+            sl['efd0'] = _real(col(g.e_fd, C128))
+        if g.exciter:
+            sl['a_vset'] = _real(col(g.exciter.v_setpoint, None))
+            sl['a_bias'] = _real(col(g.exciter.bias, None))
+        if g.governor:
+            sl['g_pref'] = _real(col(g.governor.p_ref, None))
+        out.append(sl)
+    return out

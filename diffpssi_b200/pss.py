@@ -189,8 +189,6 @@ class PowerSystemSimulation(object):
         for bus in self.busses:
             v = getattr(bus.models[-1], 'v_soll', None) if bus.models else None
             bus.voltage = v if v is not None else torch.ones((P, 1), dtype=torch.complex128, device=self.device)
-        for ev in self.param_events:
-            ev.handled = False
         self.static_y_matrix = None
         self.inverse_dynamic_y_matrix = None
 
@@ -227,8 +225,6 @@ class PowerSystemSimulation(object):
         """Everything ``run()`` does before the time loop: prologue, recorder tracing, planning, packing.
         Returns a :class:`PreparedRun` whose ``launch()`` enqueues the kernels (used by bench.py to time the loop
         alone, as the reference's own timer does -- simulator.py:507, 548-550)."""
-        if self.param_events:
-            raise NotImplementedError('ParamEvent scheduling is not part of this round (SURVEY.md section 8f.3)')
         init = self.initialize()
         P, dev = self.parallel_sims, self.device
         rplan = self._trace_recorder(init)
@@ -242,6 +238,7 @@ class PowerSystemSimulation(object):
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
+        topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary)
         plan = engine.Plan(topo)
         self.last_plan = plan
         with torch.no_grad():
@@ -251,12 +248,20 @@ class PowerSystemSimulation(object):
                                dtype=torch.float64, device=dev)
         return PreparedRun(self, init, rplan, plan, topo, extras, x0, upar, vpar, (z_re, z_im, yd_re, yd_im), zsub)
 
-    def run(self):
-        """Initialise, integrate every step of every trajectory on the GPU, return (time, result[P,T,n])."""
+    def run(self, host_out=None, stream_chunks=8):
+        """Initialise, integrate every step of every trajectory on the GPU, return (time, result[P,T,n]).
+
+        ``host_out`` (extension): a pinned host tensor ``[n_values, T, P]``; the recorder is then streamed to it in
+        ``stream_chunks`` time slices while later steps are still being integrated, and the returned result is a view of
+        ``host_out`` (no autograd)."""
         t0 = _time.time()
         prep = self.prepare()
         t1 = _time.time()
-        result, x_final = prep.execute()
+        pending = [ev for ev in self.param_events if not ev.handled]
+        if pending or host_out is not None:
+            result, x_final = prep.execute_ranges(pending, host_out, stream_chunks)
+        else:
+            result, x_final = prep.execute()
         if self.verbose:
             torch.cuda.synchronize()
             print('Dynamic simulation finished in {:.2f} seconds'.format(_time.time() - t1))
@@ -309,10 +314,79 @@ class PreparedRun(object):
         with torch.no_grad():
             self.reduce_network()
         rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, self.zsub)
+        return self._assemble(rec), x_final
+
+    def _assemble(self, rec):
         rows = self.extras['key_rows']
         if rows != list(range(rec.shape[0])):
             rec = rec[torch.tensor(rows, device=rec.device)]
-        return self.rplan.assemble(rec), x_final
+        return self.rplan.assemble(rec)
+
+    def execute_ranges(self, param_events, host_out=None, stream_chunks=8):
+        """The time loop as a sequence of step ranges (``dps_forward_range``), for two purposes:
+
+        * **parameter events** (``ParamEvent``, static_models.py:52-95; applied at simulator.py:533-534 before the solver
+          step of the first grid time ``t >= start_time``): the run is cut at those steps, the attribute is set, the
+          constant slots are re-derived and the next range continues from the carried state.  Like the reference, nothing
+          is re-initialised and Z is not rebuilt;
+        * **streaming the recorder to the host**: each finished range is copied to ``host_out`` on a second stream while
+          the next range is being integrated.
+        No autograd through this path."""
+        engine.require_cuda()
+        sim, topo = self.sim, self.topo
+        if torch.is_grad_enabled() and (self.x0.requires_grad or self.upar.requires_grad or
+                                        (self.vpar is not None and self.vpar.requires_grad)):
+            raise NotImplementedError('gradients through parameter events / streamed runs are not supported')
+        P, T, dev = sim.parallel_sims, topo['n_steps'], sim.device
+        cuts = {0, T}
+        when = {}
+        for ev in param_events:
+            hit = [k for k, t in enumerate(sim.time) if t >= ev.start_time]      # ParamEvent.handle_event: t >= start
+            if hit:
+                cuts.add(hit[0])
+                when.setdefault(hit[0], []).append(ev)
+        if host_out is not None:
+            n = max(int(stream_chunks), 1)
+            cuts |= {(T * i) // n for i in range(1, n)}
+        cuts = sorted(cuts)
+        with torch.no_grad():
+            self.reduce_network()
+            rec = torch.empty((len(topo['rec']), T, P), dtype=torch.float64, device=dev)
+            x_cur = self.x0.detach().clone()
+            plan, upar, vpar = self.plan, self.upar.detach(), None if self.vpar is None else self.vpar.detach()
+            slots = self.init.slots
+            copy_stream = torch.cuda.Stream() if host_out is not None else None
+            main = torch.cuda.current_stream()
+            rows = self.extras['key_rows']
+            for k0, k1 in zip(cuts[:-1], cuts[1:]):
+                if k0 in when:
+                    for ev in when[k0]:
+                        setattr(ev.model, ev.param_name, ev.value)
+                        ev.handled = True
+                    slots = prologue.refresh_loop_slots(sim, self.init, dev)
+                    saved, self.init.slots = self.init.slots, slots
+                    upar, vpar, slot_vary = planning.pack_slots(self.init, P, dev)
+                    t2 = dict(topo, slot_vary=slot_vary, n_vary=0 if vpar is None else vpar.shape[0], ckpt_stride=0,
+                              want=None)
+                    t2['common_ctrl'] = planning.common_controller_constants(self.init, upar, slot_vary)
+                    self.init.slots = saved
+                    plan = engine.Plan(t2)
+                plan.forward_range(P, k0, k1, x_cur, upar, vpar, self.zsub, rec, x_cur, None)
+                if host_out is not None:
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    copy_stream.wait_event(done)
+                    with torch.cuda.stream(copy_stream):
+                        for i, r in enumerate(rows):
+                            host_out[i, k0:k1].copy_(rec[r, k0:k1], non_blocking=True)
+            if host_out is not None:
+                main.wait_stream(copy_stream)
+                torch.cuda.synchronize()
+                index = {k: i for i, k in enumerate(self.rplan.channel_keys)}
+                if not self.rplan.direct:
+                    return self.rplan.assemble(host_out), x_cur
+                return host_out.permute(2, 1, 0), x_cur
+        return self._assemble(rec), x_cur
 
 
 Pss = PowerSystemSimulation

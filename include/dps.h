@@ -104,6 +104,10 @@ typedef struct {
     int32_t n_rec;
     const dps_channel* rec;   /* [n_rec] recorder selectors */
     int32_t ckpt_stride;      /* 0 = none; else states are checkpointed every ckpt_stride steps (adjoint) */
+    const double* common_ctrl;/* optional HOST [DPS_N_SLOTS]: when every generator carries all three controllers with
+                                 batch-uniform constants that are also identical between generators, their values
+                                 (slots >= DPS_N_REG_SLOTS are read); the stepper then takes them as immediate
+                                 constant-bank operands instead of shared-memory loads.  NULL otherwise. */
 } dps_topology;
 
 typedef struct dps_plan dps_plan;
@@ -161,18 +165,30 @@ int dps_forward(const dps_plan* plan, int64_t P,
                 double* rec, double* x_final, double* ckpt, void* stream);
 
 /*
+ * Same as dps_forward for the step range [step_begin, step_end) only, starting from the state `x_in` (the state before
+ * step `step_begin`) and leaving the state after step `step_end - 1` in `x_out` (may alias x_in).  `rec` and `ckpt` are
+ * the full-run buffers; only the rows of the range are written.  Used to stream the recorder to the host while later
+ * steps are still being integrated, and to apply parameter events between ranges
+ * (ParamEvent.handle_event, static_models.py:82-95, simulator.py:533-534).
+ */
+int dps_forward_range(const dps_plan* plan, int64_t P, int32_t step_begin, int32_t step_end,
+                      const double* x_in, const double* upar, const double* vpar, const double* zsub,
+                      double* rec, double* x_out, double* ckpt, void* stream);
+
+/*
  * Discrete adjoint of dps_forward (what torch autograd does for the reference in
  * optimization_lib/ps_optimization.py:212).  Recomputes each checkpoint segment forward, then sweeps it
  * backwards.  Gradients are with respect to the kernel inputs; the host chains them into the torch graph of
  * the prologue.  Z is treated as constant (parameters that enter Y_dyn are not differentiable yet).
  *
- *   grad_rec  [n_rec][n_steps][P]   dL/d rec
- *   g_x0      out [n_gen][DPS_N_STATES][P]
- *   g_upar    out [P][n_gen][DPS_N_SLOTS]   per-sim gradient of the uniform constants (host sums over p when the
- *                                           parameter really is shared) -- only slots listed in want_upar
- *   g_vpar    out [n_vary][P]
- *   want      HOST [n_gen*DPS_N_SLOTS] nonzero where a slot gradient is required
- *   gslot     out [n_want][P]  gradient of every wanted slot, in the order they appear in `want`
+ *   ckpt          [n_ckpt][n_gen][DPS_N_STATES][P]  checkpoints written by dps_forward (ckpt_stride > 0)
+ *   grad_rec      [n_rec][n_steps][P]   dL/d rec
+ *   grad_x_final  [n_gen][DPS_N_STATES][P] dL/d x_final, or NULL
+ *   want          HOST [n_gen*DPS_N_SLOTS] nonzero where a constant-slot gradient is required
+ *   g_x0          out [n_gen][DPS_N_STATES][P]
+ *   gslot         out [n_want][P]  per-trajectory gradient of every wanted slot, in the order they appear in `want`
+ *                 (the host sums over p when the slot really is shared by the batch); may be NULL if nothing is wanted
+ *   workspace     device scratch of dps_workspace_bytes(plan, P) bytes
  */
 int dps_backward(const dps_plan* plan, int64_t P,
                  const double* upar, const double* vpar, const double* zsub, const double* ckpt,

@@ -169,6 +169,29 @@ def batch_cases(sel):
         save_case(name, t, rec, names, snap, events, 'rk4', stride=1)
 
 
+def param_event_cases(sel):
+    """ParamEvent (static_models.py:52-95): an attribute is overwritten mid-run, nothing is re-initialised."""
+    name = 'ibb_param_event_heun'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['ibb'])
+        events = [(0.5, 0.55, 'Bus 1')]
+        pev = [(1.0, ('gen', 'Gen 1', 'd'), 2.0), (1.5, ('gen', 'Gen 1', 'h'), 5.0)]
+        sim, _ = rh.build(grid, 2, 'heun', DT, 3.0, events, param_events=pev)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'param_events': np.array(json.dumps([[t_, '|'.join(p_[1:]), v_] for t_, p_, v_ in pev]))}
+        save_case(name, t, rec, names, snap, events, 'heun', extra, stride=2)
+    name = 'k2a_param_event_rk4'
+    if not sel or any(s in name for s in sel):
+        grid = rh.load_example_grid(*GRIDS['k2a'])
+        events = [(0.2, 0.3, 'B1')]
+        pev = [(0.5, ('gen', 'G1', 'exciter.pt1_lim.gain_pt1'), 50.0), (0.5, ('gen', 'G3', 'stabilizer.washout.k_w'), 20.0),
+               (1.0, ('gen', 'G2', 'governor.d_t'), 0.5)]
+        sim, _ = rh.build(grid, 1, 'rk4', DT, 2.0, events, param_events=pev)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'param_events': np.array(json.dumps([[t_, '|'.join(p_[1:]), v_] for t_, p_, v_ in pev]))}
+        save_case(name, t, rec, names, snap, events, 'rk4', extra, stride=2)
+
+
 def grad_cases(sel):
     """Gradient known-answer vectors.  The reference's tests pin no gradient values
     (tests/integration/test_example_opts.py asserts nothing), so these come from the reference's own
@@ -260,6 +283,7 @@ def main():
         os.chmod(os.path.join(GOLD, 'ref_' + ref + '.npy'), 0o644)
     example_cases(sel)
     batch_cases(sel)
+    param_event_cases(sel)
     grad_cases(sel)
 
 

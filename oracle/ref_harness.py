@@ -133,7 +133,7 @@ def record_everything(sim):
 
 
 def build(grid, P, solver, dt, sim_time, events=(), overrides=None, requires_grad=False,
-          backend='torch'):
+          backend='torch', param_events=()):
     """Build a reference simulation.  ``overrides`` = {('gen', name, attr): array[P]} replaces
     model attributes by complex128 [P,1] tensors exactly like examples/models/ibb_model/ibb_opt.py:48-57."""
     simulator = _import_reference(backend)
@@ -167,6 +167,17 @@ def build(grid, P, solver, dt, sim_time, events=(), overrides=None, requires_gra
                 t = arr.astype(np.complex128) if np.iscomplexobj(old) else arr
             setattr(obj, attr, t)
             leaves[path] = t
+    # parameter events (simulator.py:464-474): (time, ('gen', name, attr), value) -> setattr at the first t >= time
+    for (t_ev, path, value) in param_events:
+        obj, attr = resolve(sim, path)
+        old = getattr(obj, attr)
+        if backend == 'torch':
+            import torch
+            dt_ = old.dtype if torch.is_tensor(old) else torch.float64
+            new = torch.ones((P, 1), dtype=dt_) * value
+        else:
+            new = np.ones((P, 1)) * value
+        sim.add_param_event(t_ev, obj, attr, new)
     return sim, leaves
 
 

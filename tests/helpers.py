@@ -75,6 +75,13 @@ def sim_from_gold(case, grid_name, device=None, requires_grad=False, sim_time=No
         sim.add_sc_event(t0, t1, b)
     ov = {k: np.tile(v, tile) for k, v in gold_overrides(gold).items()}
     leaves = apply_overrides(sim, ov, requires_grad=requires_grad)
+    if 'param_events' in gold.files:
+        for t_ev, path, value in json.loads(str(gold['param_events'])):
+            gname, attr = path.split('|', 1)
+            obj, name = resolve_attr(sim, gname, attr)
+            old = getattr(obj, name)
+            dt_ = old.dtype if torch.is_tensor(old) else torch.float64
+            sim.add_param_event(t_ev, obj, name, torch.ones((P, 1), dtype=dt_, device=sim.device) * value)
     sim.set_record_channels([str(s) for s in gold['names']])
     return sim, gold, leaves
 
@@ -126,11 +133,36 @@ def run_emulated(sim):
     x_final = np.zeros((G, engine.N_STATES, P))
     step_cfg = np.asarray(topo['step_cfg'], dtype=np.uint8)
     flat_ch = [v for c in chans for v in c]
-    lib.emul_forward(G, topo['solver'], T, ctypes.c_double(topo['dt']), ctypes.c_double(topo['fn']),
-                     (ci * G)(*topo['ctrl']), topo['n_obs'], topo['z_rows'], topo['z_cols'], topo['n_cfg'],
-                     _p(step_cfg), topo['z_per_sim'], (ci * len(slot_vary))(*slot_vary), len(chans),
-                     (ci * max(len(flat_ch), 1))(*flat_ch), ctypes.c_longlong(P), _p(x0), _p(upar), _p(vpar),
-                     _p(zsub), _p(rec), _p(x_final))
+    # parameter events cut the run into ranges exactly like PreparedRun.execute_ranges does on the GPU
+    from diffpssi_b200 import prologue as _prologue
+    cuts, when = {0, T}, {}
+    for ev in [e for e in sim.param_events if not e.handled]:
+        hit = [k for k, t in enumerate(sim.time) if t >= ev.start_time]
+        if hit:
+            cuts.add(hit[0])
+            when.setdefault(hit[0], []).append(ev)
+    cuts = sorted(cuts)
+    x_cur = x0
+    for k0, k1 in zip(cuts[:-1], cuts[1:]):
+        if k0 in when:
+            for ev in when[k0]:
+                setattr(ev.model, ev.param_name, ev.value)
+                ev.handled = True
+            saved, init.slots = init.slots, _prologue.refresh_loop_slots(sim, init, sim.device)
+            upar_t, vpar_t, slot_vary = planning.pack_slots(init, P, sim.device)
+            init.slots = saved
+            upar = upar_t.detach().cpu().numpy()
+            vpar = vpar_t.detach().cpu().numpy() if vpar_t is not None else None
+        n = k1 - k0
+        rec_part = np.zeros((len(chans), n, P))
+        cfg_part = np.ascontiguousarray(step_cfg[k0:k1])
+        lib.emul_forward(G, topo['solver'], n, ctypes.c_double(topo['dt']), ctypes.c_double(topo['fn']),
+                         (ci * G)(*topo['ctrl']), topo['n_obs'], topo['z_rows'], topo['z_cols'], topo['n_cfg'],
+                         _p(cfg_part), topo['z_per_sim'], (ci * len(slot_vary))(*slot_vary), len(chans),
+                         (ci * max(len(flat_ch), 1))(*flat_ch), ctypes.c_longlong(P), _p(np.ascontiguousarray(x_cur)),
+                         _p(upar), _p(vpar), _p(zsub), _p(rec_part), _p(x_final))
+        rec[:, k0:k1] = rec_part
+        x_cur = x_final.copy()
     result = rplan.assemble(torch.from_numpy(rec[extras['key_rows']])).numpy()
     return result, dict(init=init, topo=topo, extras=extras, zsub=zsub, x0=x0, upar=upar, vpar=vpar, rec=rec,
                         x_final=x_final, slot_vary=slot_vary)

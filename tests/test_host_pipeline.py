@@ -13,7 +13,7 @@ from tests import helpers
 
 CASES = [(g + '_' + s, g) for g in ('ibb', 'ibb_trans', 'ibb_wc', 'ieee9', 'k2a') for s in ('heun', 'euler', 'rk4')]
 CASES += [('k2a_batch_heun', 'k2a'), ('ieee9_persimz_heun', 'ieee9'), ('ieee9_two_events_heun', 'ieee9'),
-          ('k2a_two_events_rk4', 'k2a')]
+          ('k2a_two_events_rk4', 'k2a'), ('ibb_param_event_heun', 'ibb'), ('k2a_param_event_rk4', 'k2a')]
 
 
 @pytest.mark.parametrize('case,grid', CASES)
