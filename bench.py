@@ -289,11 +289,13 @@ def main():
         def e2e_step():
             set_parameters(sim, host_params, (0, P), dev)           # H2D from pinned host memory
             sim.reset()
-            _, result = sim.run()                                  # load flow + init + kernels (public API)
-            host_out.copy_(result.permute(2, 1, 0), non_blocking=True)   # recorder -> pinned host ([value][t][batch])
+            # public API: load flow + initialisation + kernels; the recorder is streamed into pinned host memory
+            # ([value][t][batch]) in 8 time slices while later steps are still being integrated
+            _, result = sim.run(host_out=host_out, stream_chunks=8)
             torch.cuda.synchronize()
 
-        e2e_step()
+        for _ in range(2):          # warm-up: first touches of the pinned result buffer and of the allocator's 10 GB block
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):

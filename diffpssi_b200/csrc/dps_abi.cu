@@ -232,6 +232,13 @@ int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const doub
     return 0;
 }
 
+int dps_math_probe(int64_t n, const double* a, const double* b, double* out, void* stream) {
+    if (n < 1 || !a || !b || !out) { set_error("dps_math_probe: bad argument"); return 1; }
+    cudaError_t e = launch_math_probe(n, a, b, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dps_math_probe: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
 int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds) {
     if (!tflops || !milliseconds || iters < 1) { set_error("dps_fp64_peak_probe: bad argument"); return 1; }
     cudaError_t e = run_fp64_probe(iters, tflops, milliseconds);

@@ -28,7 +28,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include "dps_internal.h"
 #include "dps_model.cuh"
 
@@ -40,9 +39,11 @@ struct FwdCfg {
     static constexpr int WARPS = 4;                // warps are independent; the block size only sets the launch geometry
     static constexpr int THREADS = 32 * WARPS;
 #ifndef DPS_MIN_BLOCKS
-#define DPS_MIN_BLOCKS 3
+#define DPS_MIN_BLOCKS 4
 #endif
-    static constexpr int MIN_BLOCKS = DPS_MIN_BLOCKS;   // 3 -> 12 warps/SM at <= 168 registers
+    static constexpr int MIN_BLOCKS = DPS_MIN_BLOCKS;   // 4 -> 16 warps/SM at <= 128 registers (measured best, profiles/)
+    // a batch-shared Z row also lives in registers while it is small; larger systems read it from shared memory
+    static constexpr bool Z_SMEM = (G > 10);
     static constexpr int UPS = DPS_N_SLOTS + 1;    // row stride of the constant table: odd -> conflict-free per-lane rows
 };
 
@@ -325,14 +326,14 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
 
 template <int G>
 cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs) {
-    // DPS_FORCE_ZREG=1 (experiments): keep the row of a batch-shared Z in registers instead of shared memory
-    static const bool force_zreg = (getenv("DPS_FORCE_ZREG") != nullptr);
-    const int zps = (p.z_per_sim || force_zreg) ? 1 : 0;
+    const int zps = (p.z_per_sim || !FwdCfg<G>::Z_SMEM) ? 1 : 0;
 #define DPS_CASE(C, M, Z)                                                                          \
-    if (cmask == C && pmode == M && zps == Z) {                                                     \
-        if (p.solver == DPS_EULER) return launch_one<G, C, M, Z, DPS_EULER>(p, stream, regs);      \
-        if (p.solver == DPS_HEUN) return launch_one<G, C, M, Z, DPS_HEUN>(p, stream, regs);        \
-        return launch_one<G, C, M, Z, DPS_RK4>(p, stream, regs);                                   \
+    if constexpr (Z == 1 || FwdCfg<G>::Z_SMEM) {                                                   \
+        if (cmask == C && pmode == M && zps == Z) {                                                \
+            if (p.solver == DPS_EULER) return launch_one<G, C, M, Z, DPS_EULER>(p, stream, regs);  \
+            if (p.solver == DPS_HEUN) return launch_one<G, C, M, Z, DPS_HEUN>(p, stream, regs);    \
+            return launch_one<G, C, M, Z, DPS_RK4>(p, stream, regs);                               \
+        }                                                                                          \
     }
     DPS_CASE(0, 1, 0) DPS_CASE(0, 1, 1) DPS_CASE(0, 2, 0) DPS_CASE(0, 2, 1)
     DPS_CASE(7, 1, 0) DPS_CASE(7, 1, 1) DPS_CASE(7, 2, 0) DPS_CASE(7, 2, 1) DPS_CASE(7, 3, 0) DPS_CASE(7, 3, 1)

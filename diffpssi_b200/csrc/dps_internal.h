@@ -60,6 +60,7 @@ struct ReduceParams {
 cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream);
 
 cudaError_t run_fp64_probe(int iters, double* tflops, double* ms);
+cudaError_t launch_math_probe(long long n, const double* a, const double* b, double* out, cudaStream_t stream);
 #endif
 
 void set_error(const char* fmt, ...);

@@ -26,27 +26,30 @@ static __constant__ double dps_trig_c[16] = {
     -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 #endif
 #ifdef __CUDA_ARCH__
+// rcp.approx / rsqrt.approx deliver >= 20 good bits; one Newton step (>= 40 bits) followed by one residual
+// correction of the final quotient / root (which doubles the accuracy again) is correctly rounded in all but a
+// vanishing fraction of cases (checked against libm by tests/test_cuda_parity.py::test_device_math).
 __device__ __forceinline__ double dps_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);                   // two Newton steps: 2^-20 -> 2^-40 -> 2^-80
+    const double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e2 = fma(-x, r, 1.0);
+    return fma(r, e2, r);
 }
 __device__ __forceinline__ double dps_div(double a, double b) {
-    const double r = dps_rcp(b);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
     const double q = a * r;
-    return fma(fma(-q, b, a), r, q);             // one residual correction
+    return fma(fma(-q, b, a), r, q);             // residual correction
 }
 __device__ __forceinline__ double dps_sqrt(double s) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    double h = 0.5 * y;
-    double e = fma(-s * y, h, 0.5);                // 0.5 - 0.5*s*y^2
-    y = fma(y, e, y);
-    h = 0.5 * y;
-    e = fma(-s * y, h, 0.5);
+    const double h = 0.5 * y;
+    const double e = fma(-s * y, h, 0.5);          // 0.5 - 0.5*s*y^2
     y = fma(y, e, y);
     const double r = s * y;
     const double res = fma(fma(-r, r, s), 0.5 * y, r);
@@ -140,11 +143,12 @@ struct Algebraics {            // values the reference keeps on the machine obje
 template <class PR>
 __device__ __forceinline__ void injection(const double* x, const PR& par, double sd, double cd,
                                           double& i_re, double& i_im) {
-    const double a = x[DPS_X_EQST] * par(DPS_S_INV_XDST);
-    const double b = x[DPS_X_EDST] * par(DPS_S_INV_XQST);
+    // the base change S_n/S_sys is folded into a and b (two multiplications fewer than scaling both components)
     const double snr = par(DPS_S_SNR);
-    i_re = (a * sd - b * cd) * snr;
-    i_im = (-(a * cd) - b * sd) * snr;
+    const double a = x[DPS_X_EQST] * (par(DPS_S_INV_XDST) * snr);
+    const double b = x[DPS_X_EDST] * (par(DPS_S_INV_XQST) * snr);
+    i_re = a * sd - b * cd;
+    i_im = -(a * cd + b * sd);
 }
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) {
@@ -153,6 +157,30 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) {
     const double m = (v < lo) ? lo : v;
     return (m > hi) ? hi : m;
 }
+
+// PT1Limited (blocks.py:138-150, 170-182): output = clamp(state, lo, hi), and the anti-windup gate freezes the
+// derivative when (state <= lo and dx < 0) or (state >= hi and dx > 0).  The two FP64 comparisons state<=lo / state>=hi
+// serve both (for lo <= hi, `state<=lo ? lo : state>=hi ? hi : state` equals minimum(maximum(state, lo), hi)); the sign
+// tests of dx are integer tests on its high word (a -0.0 derivative is frozen to +0.0, which is the same number).
+struct Pt1Lim {
+    bool le, ge;
+    double out;
+    __device__ __forceinline__ Pt1Lim(double state, double lo, double hi) {
+        le = state <= lo;
+        ge = state >= hi;
+        out = le ? lo : (ge ? hi : state);
+    }
+    __device__ __forceinline__ double gate(double dx) const {
+#ifdef __CUDA_ARCH__
+        const int hw = __double2hiint(dx), lw = __double2loint(dx);
+        const bool neg = hw < 0;
+        const bool pos = !neg && ((hw | lw) != 0);
+#else
+        const bool neg = dx < 0.0, pos = dx > 0.0;
+#endif
+        return ((le && neg) || (ge && pos)) ? 0.0 : dx;
+    }
+};
 
 // Anti-windup gate of PT1Limited.differential, blocks.py:145-149: `<=`/`>=` on the state, strict on the derivative
 __device__ __forceinline__ double windup_gate(double state, double dx, double lo, double hi) {
@@ -213,21 +241,23 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
             const double xll = x[DPS_X_AVR_LL], xe = x[DPS_X_AVR_PT1];
             const double o = par(DPS_S_A_R) * u + par(DPS_S_A_OMR) * xll;
             const double emin = par(DPS_S_A_EMIN), emax = par(DPS_S_A_EMAX);
-            e_fd = clampd(xe, emin, emax);
+            const Pt1Lim lim(xe, emin, emax);
+            e_fd = lim.out;
             f[DPS_X_AVR_LL] = par(DPS_S_A_INV_TB) * (u - xll);
             const double dxe = par(DPS_S_A_INV_TE) * (par(DPS_S_A_K) * o - xe);      // blocks.py:143
-            f[DPS_X_AVR_PT1] = windup_gate(xe, dxe, emin, emax);
+            f[DPS_X_AVR_PT1] = lim.gate(dxe);
         }
         if (ctrl & DPS_CTRL_GOV) {
             // TGOV1.get_output(omega), governors.py:115-123
             const double u = par(DPS_S_G_PREF) - omega;
             const double xg = x[DPS_X_GOV_PT1], xll = x[DPS_X_GOV_LL];
             const double vmin = par(DPS_S_G_VMIN), vmax = par(DPS_S_G_VMAX);
-            const double gs = clampd(xg, vmin, vmax);
+            const Pt1Lim lim(xg, vmin, vmax);
+            const double gs = lim.out;
             const double o = par(DPS_S_G_R) * gs + par(DPS_S_G_OMR) * xll;
             p_m = o - par(DPS_S_G_DT) * omega;
             const double dxg = par(DPS_S_G_INV_T1) * (par(DPS_S_G_GAIN) * u - xg);
-            f[DPS_X_GOV_PT1] = windup_gate(xg, dxg, vmin, vmax);
+            f[DPS_X_GOV_PT1] = lim.gate(dxg);
             f[DPS_X_GOV_LL] = par(DPS_S_G_INV_T3) * (gs - xll);
         }
     }
@@ -235,7 +265,7 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
     // synchronous_machine.py:158-164
     const double t_m = dps_div(p_m, 1.0 + omega);
     f[DPS_X_OMEGA] = par(DPS_S_INV_2H) * ((t_m - p_e) - par(DPS_S_D) * omega);
-    f[DPS_X_DELTA] = ((omega * 2.0) * 3.141592653589793) * fn;
+    f[DPS_X_DELTA] = omega * ((2.0 * 3.141592653589793) * fn);
     f[DPS_X_EQT] = par(DPS_S_INV_TD0T) * ((e_fd - x[DPS_X_EQT]) - i_d * par(DPS_S_XD_XDT));
     f[DPS_X_EDT] = par(DPS_S_INV_TQ0T) * (-x[DPS_X_EDT] + i_q * par(DPS_S_XQ_XQT));
     f[DPS_X_EQST] = par(DPS_S_INV_TD0ST) * ((x[DPS_X_EQT] - eqst) - i_d * par(DPS_S_XDT_XDST));

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "dps_internal.h"
 #include "dps_reduce.cuh"
+#include "dps_model.cuh"
 
 namespace dps {
 
@@ -43,6 +44,24 @@ __global__ void __launch_bounds__(256) dps_fp64_probe_kernel(double* out, int it
     }
     const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
     if (s == 12345.678) out[0] = s;      // never true: keeps the chains alive
+}
+
+// device math self-test: out[0..4][n] = sin(a), cos(a), a/b, sqrt(|a|), 1/b with the kernels' own primitives
+__global__ void dps_math_probe_kernel(long long n, const double* a, const double* b, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    dps_sincos(a[i], &s, &c);
+    out[i] = s;
+    out[n + i] = c;
+    out[2 * n + i] = dps_div(a[i], b[i]);
+    out[3 * n + i] = dps_sqrt(fabs(a[i]));
+    out[4 * n + i] = dps_rcp(b[i]);
+}
+
+cudaError_t launch_math_probe(long long n, const double* a, const double* b, double* out, cudaStream_t stream) {
+    dps_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, a, b, out);
+    return cudaGetLastError();
 }
 
 cudaError_t run_fp64_probe(int iters, double* tflops, double* ms_out) {

@@ -22,7 +22,7 @@ MAX_CFG = 16
 MAX_FAULT = 8
 
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes',
-           'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_plan_info',
+           'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_math_probe', 'dps_plan_info',
            'dps_last_error', 'dps_abi_version')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
@@ -82,6 +82,7 @@ def load_library(path=None):
     lib.dps_forward_range.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dps_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint8), vp, vp, vp,
                                  ctypes.c_size_t, vp]
+    lib.dps_math_probe.argtypes = [i64, vp, vp, vp, vp]
     lib.dps_fp64_peak_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     lib.dps_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     if lib.dps_abi_version() != ABI_VERSION:
@@ -189,6 +190,15 @@ def network_reduce(z_re, z_im, yd_re, yd_im, obs_bus, gen_bus, cfg_sets, y_fault
     _check(lib, lib.dps_network_reduce(Bz, n_bus, _ptr(z_re), _ptr(z_im), _ptr(yd_re), _ptr(yd_im),
                                        len(obs_bus), a_obs, len(gen_bus), a_gen, len(cfg_sets), a_ptr, a_bus,
                                        float(y_fault), _ptr(zsub), _stream()), 'dps_network_reduce')
+
+
+def math_probe(a, b):
+    """sin(a), cos(a), a/b, sqrt(|a|), 1/b computed by the kernels' own device primitives -> [5, n] tensor."""
+    require_cuda()
+    lib = load_library()
+    out = torch.empty((5, a.numel()), dtype=torch.float64, device=a.device)
+    _check(lib, lib.dps_math_probe(a.numel(), _ptr(a), _ptr(b), _ptr(out), _stream()), 'dps_math_probe')
+    return out
 
 
 def fp64_peak_probe(iters=4096):

@@ -58,8 +58,11 @@ CTRL_AVR, CTRL_GOV, CTRL_PSS = 1, 2, 4
 class _Cols(object):
     """Fetches model attributes as ``[B,1]`` tensors on the run device, collapsing batch-uniform ones."""
 
-    def __init__(self, P, device):
+    def __init__(self, P, device, cache=None):
         self.P, self.device = P, device
+        # id(tensor) -> (tensor, version): tensors already found batch-uniform.  Keeps run() from re-checking (one
+        # device sync each) the hundreds of default parameter tensors that never change between runs.
+        self.cache = cache if cache is not None else {}
 
     def __call__(self, value, dtype=None, collapse=True, last_row=False):
         P = self.P
@@ -80,7 +83,11 @@ class _Cols(object):
         if last_row:
             return t[-1:]
         if collapse and t.shape[0] == P and P > 1 and not t.requires_grad:
+            hit = self.cache.get(id(value))
+            if hit is not None and hit[0] is value and hit[1] == value._version:
+                return t[:1]
             if bool((t == t[:1]).all()):
+                self.cache[id(value)] = (value, value._version)
                 return t[:1]
         return t
 
@@ -138,12 +145,11 @@ def _assemble(sim, col, diag_contrib):
         for v in contribs:
             add(i, i, v)
     B = max([v.shape[0] for v in entries.values()] + [1])
-    zero = torch.zeros(B, dtype=C128, device=col.device)
-    rows = []
-    for i in range(n):
-        rows.append(torch.stack([entries[(i, j)].expand(B) if (i, j) in entries else zero for j in range(n)],
-                                dim=-1))
-    return torch.stack(rows, dim=-2)
+    keys = sorted(entries)
+    flat = torch.tensor([i * n + j for i, j in keys], dtype=torch.long, device=col.device)
+    vals = torch.stack([entries[k].expand(B) for k in keys], dim=1)                       # [B, nnz]
+    y = torch.zeros((B, n * n), dtype=C128, device=col.device).index_copy(1, flat, vals)
+    return y.reshape(B, n, n)
 
 
 def static_admittance(sim, col):
@@ -230,14 +236,10 @@ def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
         rhs = torch.cat([err.real[:, ia], err.imag[:, iq]], dim=1).unsqueeze(-1)
         dx = torch.linalg.solve(-J, rhs).squeeze(-1)                           # [B, n_ang + n_pq]
         # update: angles of PV and PQ buses, then magnitudes of PQ buses (load_flow.py:150-158)
-        cols = [V[:, i] for i in range(n)]
-        for k, b in enumerate(ang_ids):
-            v = cols[b]
-            cols[b] = torch.abs(v) * torch.exp(1j * (torch.angle(v) - dx[:, k]))
-        for k, b in enumerate(pq):
-            v = cols[b]
-            cols[b] = (torch.abs(v) - dx[:, n_ang + k]) * torch.exp(1j * torch.angle(v))
-        V = torch.stack(cols, dim=1)
+        va = V[:, ia]
+        V = V.index_copy(1, ia, torch.abs(va) * torch.exp(1j * (torch.angle(va) - dx[:, :n_ang])))
+        vq = V[:, iq]
+        V = V.index_copy(1, iq, (torch.abs(vq) - dx[:, n_ang:]) * torch.exp(1j * torch.angle(vq)))
         worst = float(torch.max(torch.abs(rhs)))
         if worst < tol:
             break
@@ -264,7 +266,7 @@ def initialize(sim, device):
     """Load flow + model initialisation + Z = inv(Y_dyn) + initial bus voltages.
     Mirrors simulator.py:438-450.  Everything returned is ``[B,1]`` (B in {1,P}) real float64, except Z0/Ydiag/bus_v."""
     P = sim.parallel_sims
-    col = _Cols(P, device)
+    col = _Cols(P, device, getattr(sim, '_uniform_cache', None))
     res = InitResult()
     y_static = static_admittance(sim, col)
     V, s_calc, iters = load_flow(sim, col, y_static)
@@ -403,7 +405,7 @@ def refresh_loop_slots(sim, init, device):
     simulator.py:533-534).  The reference only ``setattr``s: nothing is re-initialised, so the values initialize() left
     behind (p_m / e_fd of uncontrolled machines, v_setpoint, bias, p_ref) and Z stay as they are; every other constant
     is re-derived from the current attributes with the same expressions as in :func:`initialize`."""
-    col = _Cols(sim.parallel_sims, device)
+    col = _Cols(sim.parallel_sims, device, getattr(sim, '_uniform_cache', None))
     out = []
     for g, old in zip(init.gens, init.slots):
         c = {k: col(getattr(g, k), C128) for k in ('s_n', 'h', 'd', 'x_d', 'x_q', 'x_d_t', 'x_q_t', 'x_d_st', 'x_q_st',

@@ -67,6 +67,7 @@ class PowerSystemSimulation(object):
         self.base_voltage = self.base_mva = self.fn = None
         self.last_init = None
         self.last_plan = None
+        self._uniform_cache = {}
         self.timings = {}
         if grid_data is not None:
             self.create_grid(grid_data)

@@ -201,6 +201,10 @@ int dps_backward(const dps_plan* plan, int64_t P,
  * (MEASURED_PEAKS.json has no fp64 entry). */
 int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds);
 
+/* Test helper: evaluates the kernels' own branch-free math primitives on the device,
+ * out[0..4][n] = sin(a), cos(a), a/b, sqrt(|a|), 1/b  (a, b, out: device arrays). */
+int dps_math_probe(int64_t n, const double* a, const double* b, double* out, void* stream);
+
 /* Static information about the specialisation a plan selected (for logs / bench "gpu_launches"). */
 int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_per_block, int32_t* regs_per_thread,
                   int32_t* g_template);

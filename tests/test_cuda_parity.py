@@ -147,3 +147,35 @@ def test_determinism_and_rerun_after_reset():
 def test_fp64_probe_runs():
     tf, ms = engine.fp64_peak_probe(2048)
     assert 5.0 < tf < 80.0, tf
+
+
+def test_streamed_recorder_equals_plain_run():
+    """run(host_out=...) cuts the loop into step ranges (dps_forward_range) and streams the recorder to pinned host
+    memory; the trajectories must be bit-identical to the single-launch run."""
+    sim, gold, _ = helpers.sim_from_gold('k2a_heun', 'k2a', device='cuda', P=70, sim_time=2.0)
+    _, a = sim.run()
+    sim.reset()
+    host = torch.empty((len(gold['names']), len(sim.time), 70), dtype=torch.float64).pin_memory()
+    _, b = sim.run(host_out=host, stream_chunks=7)
+    assert not b.is_cuda and tuple(b.shape) == tuple(a.shape)
+    assert torch.equal(a.cpu(), b)
+
+
+def test_device_math():
+    """The branch-free sincos / division / sqrt the kernels use, against numpy (libm): <= 2 ulp."""
+    rng = np.random.RandomState(3)
+    a = np.concatenate([rng.uniform(-200.0, 200.0, 200000), rng.uniform(-1e-3, 1e-3, 1000), rng.uniform(-3e4, 3e4, 20000),
+                        np.array([0.0, 1e-300, np.pi / 2, -np.pi / 4, 1.0])])
+    b = np.concatenate([rng.uniform(0.2, 3.0, a.size - 5) * rng.choice([-1.0, 1.0], a.size - 5),
+                        np.array([1.0, 3.0, 1e-3, 7.0, 1e6])])
+    out = engine.math_probe(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    eps = np.finfo(np.float64).eps
+
+    def ulps(x, ref, floor=0.0):
+        return np.abs(x - ref) / (eps * np.maximum(np.abs(ref), floor))
+
+    assert ulps(out[0], np.sin(a), 1e-3).max() < 4 and ulps(out[1], np.cos(a), 1e-3).max() < 4
+    assert np.abs(out[0] - np.sin(a)).max() < 1e-15 and np.abs(out[1] - np.cos(a)).max() < 1e-15
+    assert ulps(out[2], a / b, 1e-300).max() <= 1.0
+    assert ulps(out[3], np.sqrt(np.abs(a)), 1e-300).max() <= 1.0
+    assert ulps(out[4], 1.0 / b).max() <= 1.0
