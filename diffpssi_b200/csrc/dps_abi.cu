@@ -35,8 +35,17 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
     if (!t || !out) { set_error("dps_plan_create: null argument"); return 1; }
     if (t->abi_version != DPS_ABI_VERSION) { set_error("dps_plan_create: ABI version %d != %d", t->abi_version, DPS_ABI_VERSION); return 1; }
     if (t->n_gen < 1) { set_error("dps_plan_create: n_gen must be >= 1"); return 1; }
-    if (t->n_gen > MAX_G) {
-        set_error("dps_plan_create: %d generators exceed the register-resident stepper limit (%d)", t->n_gen, MAX_G);
+    if (t->n_gen > MAX_GW) {
+        set_error("dps_plan_create: %d generators exceed the stepper limit (%d)", t->n_gen, MAX_GW);
+        return 2;
+    }
+    const bool wide = t->n_gen > MAX_G;
+    if (wide && t->z_per_sim) {
+        set_error("dps_plan_create: systems with more than %d generators need a network shared by the batch", MAX_G);
+        return 2;
+    }
+    if (wide && t->ckpt_stride > 0) {
+        set_error("dps_plan_create: the adjoint is not available for systems with more than %d generators", MAX_G);
         return 2;
     }
     if (t->solver < DPS_EULER || t->solver > DPS_RK4) { set_error("dps_plan_create: unknown solver %d", t->solver); return 1; }
@@ -64,7 +73,8 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
     }
     if (pl->seg_step.empty()) { pl->seg_step.push_back(0); pl->seg_cfg.push_back(0); }
 
-    pl->g_template = fwd_template_g(t->n_gen);
+    pl->wide = wide;
+    pl->g_template = wide ? t->n_gen : fwd_template_g(t->n_gen);
     pl->any_ctrl = false;
     pl->any_vary = false;
     for (int g = 0; g < t->n_gen; ++g) pl->any_ctrl |= (pl->ctrl[g] != 0);
@@ -83,33 +93,50 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
             if (pl->slot_vary[(size_t)g * DPS_N_SLOTS + k] >= 0) pl->pmode = 2;
 
     FwdParams& b = pl->base;
+    WideParams& w = pl->wbase;
     memset(&b, 0, sizeof(b));
+    memset(&w, 0, sizeof(w));
     if (t->common_ctrl != nullptr && pl->pmode == 1 && pl->cmask == 7) {
         pl->pmode = 3;
-        for (int k = 0; k < DPS_N_SLOTS; ++k) b.cpar[k] = t->common_ctrl[k];
+        for (int k = 0; k < DPS_N_SLOTS; ++k) b.cpar[k] = w.cpar[k] = t->common_ctrl[k];
+    }
+    if (wide && pl->pmode == 2) {
+        set_error("dps_plan_create: with more than %d generators only the machine constants and set points may differ per trajectory", MAX_G);
+        delete pl; return 2;
     }
     b.n_gen = t->n_gen; b.solver = t->solver; b.n_steps = t->n_steps; b.dt = t->dt; b.fn = t->fn;
     b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.n_cfg = t->n_cfg; b.z_per_sim = t->z_per_sim;
     b.ckpt_stride = t->ckpt_stride;
-    for (int g = 0; g < t->n_gen; ++g) b.ctrl[g] = pl->ctrl[g];
-    for (size_t i = 0; i < pl->slot_vary.size(); ++i) b.slot_vary[i] = (short)pl->slot_vary[i];
-    for (int e = 0; e < MAX_EXTRA_OBS; ++e) b.obs_chan[e][0] = b.obs_chan[e][1] = -1;
+    w.n_gen = t->n_gen; w.solver = t->solver; w.n_steps = t->n_steps; w.dt = t->dt; w.fn = t->fn;
+    w.n_obs = t->n_obs; w.z_rows = t->z_rows; w.z_cols = t->z_cols; w.n_cfg = t->n_cfg; w.z_per_sim = t->z_per_sim;
+    w.ckpt_stride = t->ckpt_stride;
+    for (int g = 0; g < t->n_gen; ++g) {
+        if (wide) {
+            w.ctrl[g] = (unsigned char)pl->ctrl[g];
+            for (int k = 0; k < DPS_N_REG_SLOTS; ++k) w.reg_vary[g][k] = (short)pl->slot_vary[(size_t)g * DPS_N_SLOTS + k];
+        } else {
+            b.ctrl[g] = pl->ctrl[g];
+            for (int k = 0; k < DPS_N_SLOTS; ++k) b.slot_vary[g * DPS_N_SLOTS + k] = (short)pl->slot_vary[(size_t)g * DPS_N_SLOTS + k];
+        }
+    }
+    for (int e = 0; e < MAX_EXTRA_OBS; ++e) b.obs_chan[e][0] = b.obs_chan[e][1] = w.obs_chan[e][0] = w.obs_chan[e][1] = -1;
     for (int c = 0; c < t->n_rec; ++c) {
         const dps_channel& ch = pl->rec[c];
         if (ch.kind == DPS_CH_GEN) {
             if (ch.index < 0 || ch.index >= t->n_gen || ch.field < 0 || ch.field >= DPS_N_FIELDS) {
                 set_error("dps_plan_create: recorder channel %d out of range", c); delete pl; return 1;
             }
-            if (b.rec_mask[ch.index] & (1u << ch.field)) {
+            unsigned& mask = wide ? w.rec_mask[ch.index] : b.rec_mask[ch.index];
+            if (mask & (1u << ch.field)) {
                 set_error("dps_plan_create: recorder channel %d duplicates generator %d field %d", c, ch.index, ch.field);
                 delete pl; return 1;
             }
-            b.rec_mask[ch.index] |= (1u << ch.field);
-            b.rec_chan[ch.index][ch.field] = (short)c;
+            mask |= (1u << ch.field);
+            (wide ? w.rec_chan[ch.index][ch.field] : b.rec_chan[ch.index][ch.field]) = (short)c;
         } else if (ch.kind == DPS_CH_BUS_VRE || ch.kind == DPS_CH_BUS_VIM) {
             const int e = ch.index - t->n_gen;
             if (e < 0 || ch.index >= t->n_obs) { set_error("dps_plan_create: bus channel %d must name an extra observed row", c); delete pl; return 1; }
-            short& slot = b.obs_chan[e][ch.kind == DPS_CH_BUS_VIM];
+            short& slot = wide ? w.obs_chan[e][ch.kind == DPS_CH_BUS_VIM] : b.obs_chan[e][ch.kind == DPS_CH_BUS_VIM];
             if (slot >= 0) { set_error("dps_plan_create: recorder channel %d duplicates an observed-bus channel", c); delete pl; return 1; }
             slot = (short)c;
         } else {
@@ -133,17 +160,21 @@ int64_t dps_n_checkpoints(const dps_plan* plan) {
 int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_per_block, int32_t* regs_per_thread,
                   int32_t* g_template) {
     if (!plan) { set_error("dps_plan_info: null plan"); return 1; }
-    int th = 0, spb = 0;
-    fwd_geometry(plan->g_template, &th, &spb);
+    int th = 0, spb = 0, regs = 0;
+    if (plan->wide) {
+        cudaError_t e = launch_forward_wide(plan->wbase, plan->cmask, plan->pmode, 0, &regs, &th, &spb);
+        if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
+    } else {
+        fwd_geometry(plan->g_template, &th, &spb);
+        if (regs_per_thread) {
+            cudaError_t e = launch_forward(plan->base, plan->g_template, plan->cmask, plan->pmode, 0, &regs);
+            if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
+        }
+    }
     if (block_threads) *block_threads = th;
     if (sims_per_block) *sims_per_block = spb;
     if (g_template) *g_template = plan->g_template;
-    if (regs_per_thread) {
-        int regs = 0;
-        cudaError_t e = launch_forward(plan->base, plan->g_template, plan->cmask, plan->pmode, 0, &regs);
-        if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
-        *regs_per_thread = regs;
-    }
+    if (regs_per_thread) *regs_per_thread = regs;
     return 0;
 }
 
@@ -170,16 +201,21 @@ static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int st
         int seg1 = seg0 + 1;
         while (seg1 < n_seg && seg1 - seg0 < MAX_SEG && plan->seg_step[seg1] < step_end) ++seg1;
         const int end = (seg1 < n_seg && plan->seg_step[seg1] < step_end) ? plan->seg_step[seg1] : step_end;
-        FwdParams p = plan->base;
-        p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub;
-        p.rec = rec; p.ckpt = ckpt;
-        p.step_begin = begin;
-        p.step_end = end;
-        p.n_seg = seg1 - seg0;
-        for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
         if (end < step_end && !x_out) { set_error("%s: more than %d configuration changes need x_final as carry buffer", who, MAX_SEG); return 1; }
-        p.x_final = x_out;
-        cudaError_t e = launch_forward(p, plan->g_template, plan->cmask, plan->pmode, st, nullptr);
+        cudaError_t e;
+        if (plan->wide) {
+            WideParams p = plan->wbase;
+            p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.rec = rec; p.ckpt = ckpt; p.x_final = x_out;
+            p.step_begin = begin; p.step_end = end; p.n_seg = seg1 - seg0;
+            for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
+            e = launch_forward_wide(p, plan->cmask, plan->pmode, st, nullptr, nullptr, nullptr);
+        } else {
+            FwdParams p = plan->base;
+            p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.rec = rec; p.ckpt = ckpt; p.x_final = x_out;
+            p.step_begin = begin; p.step_end = end; p.n_seg = seg1 - seg0;
+            for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
+            e = launch_forward(p, plan->g_template, plan->cmask, plan->pmode, st, nullptr);
+        }
         if (e != cudaSuccess) { set_error("%s: launch failed: %s", who, cudaGetErrorString(e)); return 3; }
         x_in = x_out;
         begin = end;
@@ -206,7 +242,7 @@ int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const doub
                        void* stream) {
     if (!z_re || !z_im || !yd_re || !yd_im || !obs_bus || !gen_bus || !cfg_ptr || !zsub) { set_error("dps_network_reduce: null argument"); return 1; }
     if (Bz < 1 || n_bus < 1) { set_error("dps_network_reduce: bad sizes"); return 1; }
-    if (n_gen < 1 || n_gen > MAX_G || n_obs < n_gen || n_obs > MAX_G + MAX_EXTRA_OBS) { set_error("dps_network_reduce: n_gen/n_obs out of range"); return 1; }
+    if (n_gen < 1 || n_gen > MAX_GW || n_obs < n_gen || n_obs > MAX_GW + MAX_EXTRA_OBS) { set_error("dps_network_reduce: n_gen/n_obs out of range"); return 1; }
     if (n_cfg < 1 || n_cfg > RED_MAX_CFG) { set_error("dps_network_reduce: n_cfg %d out of range (max %d)", n_cfg, RED_MAX_CFG); return 1; }
     ReduceParams p;
     memset(&p, 0, sizeof(p));

@@ -8,7 +8,8 @@
 
 namespace dps {
 
-constexpr int MAX_G = 16;            // generators handled by the register-resident stepper
+constexpr int MAX_G = 16;            // generators handled by the warp-exchange stepper (dps_forward.cuh)
+constexpr int MAX_GW = 128;          // generators handled by the wide stepper (dps_forward_wide.cuh)
 constexpr int MAX_SEG = 48;          // network-configuration change points per launch
 constexpr int MAX_EXTRA_OBS = 24;    // recorded non-generator buses
 
@@ -35,11 +36,36 @@ struct FwdParams {
     double cpar[DPS_N_SLOTS];               // PMODE 3: controller constants common to all generators
 };
 
+// Parameter block of the wide stepper: same scalars, tables sized for MAX_GW generators (~11 KB, passed by value).
+struct WideParams {
+    long long P;
+    int n_gen, solver, n_steps, step_begin, step_end;
+    double dt, fn;
+    const double* x0;
+    const double* upar;
+    const double* vpar;
+    const double* zsub;
+    double* rec;
+    double* x_final;
+    double* ckpt;
+    int n_obs, z_rows, z_cols, n_cfg, z_per_sim, ckpt_stride, n_seg;
+    int seg_step[MAX_SEG];
+    int seg_cfg[MAX_SEG];
+    unsigned char ctrl[MAX_GW];
+    unsigned rec_mask[MAX_GW];
+    short rec_chan[MAX_GW][DPS_N_FIELDS];
+    short obs_chan[MAX_EXTRA_OBS][2];
+    short reg_vary[MAX_GW][DPS_N_REG_SLOTS];   // row of vpar or -1, leading (register) slots only
+    double cpar[DPS_N_SLOTS];
+};
+
 int fwd_template_g(int n_gen);
 void fwd_geometry(int g_template, int* threads, int* sims_per_block);
 #ifdef __CUDACC__
 cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream,
                            int* regs_query);
+cudaError_t launch_forward_wide(const WideParams& p, int cmask, int pmode, cudaStream_t stream, int* regs_query,
+                                int* threads, int* sims_per_block);
 #endif
 
 constexpr int RED_MAX_CFG = 16;      // distinct faulted-bus sets per run
@@ -51,8 +77,8 @@ struct ReduceParams {
     double y_fault;
     const double *z_re, *z_im, *yd_re, *yd_im;
     double* zsub;
-    int obs_bus[MAX_G + MAX_EXTRA_OBS];
-    int gen_bus[MAX_G];
+    int obs_bus[MAX_GW + MAX_EXTRA_OBS];
+    int gen_bus[MAX_GW];
     int cfg_n[RED_MAX_CFG];
     int cfg_bus[RED_MAX_CFG][RED_MAX_FAULT];
 };

@@ -14,5 +14,7 @@ struct dps_plan {
     bool any_ctrl, any_vary;
     int cmask;                            // common controller flag set of all generators (0 or 7), or -1 if mixed
     int pmode;                            // 1 = machine constants in registers, 2 = generic slot table
+    bool wide;                            // more than MAX_G generators: dps_step_wide_kernel
+    dps::WideParams wbase;
     dps::FwdParams base;                       // everything that does not depend on the call
 };

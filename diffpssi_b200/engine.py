@@ -16,7 +16,8 @@ ABI_VERSION = 1
 N_STATES = 13
 N_SLOTS = 42
 N_FIELDS = 20
-MAX_G = 16
+MAX_G = 16          # warp-exchange stepper
+MAX_GW = 128        # wide stepper
 MAX_EXTRA_OBS = 24
 MAX_CFG = 16
 MAX_FAULT = 8

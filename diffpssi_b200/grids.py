@@ -87,3 +87,44 @@ GENERATOR_NOMINALS = {
         (3.45, 0.32), (5.00, 0.30)])},
     'k2a': {'G1': (6.5, 0.3), 'G2': (6.5, 0.3), 'G3': (6.175, 0.3), 'G4': (6.175, 0.3)},
 }
+
+
+def tiled(n_cells=100, ring_stride=10):
+    """Synthetic tiled grid for BASELINE.json config 5: ``n_cells`` identical 5-bus / 1-generator cells (500 buses and
+    100 generators for the default) with all three controllers on every machine, cells tied into a ring plus a second
+    ring with stride ``ring_stride`` (a torus-like mesh).  The network is shared by the batch; H, D, X_d' may vary.
+
+    Cell c: G<c> (generator, 20 kV) --T-- H<c> (230 kV) -- A<c>, B<c> (loads) -- X<c> (tie bus);
+    ties: X<c> -- H<c+1>  and  X<c> -- X<c+ring_stride>  (indices modulo n_cells).
+    """
+    n = n_cells
+    busses, lines, trafos, loads, gens = [], [], [], [], []
+    for c in range(n):
+        busses += [['G%d' % c, 20], ['H%d' % c, 230], ['A%d' % c, 230], ['B%d' % c, 230], ['X%d' % c, 230]]
+        trafos.append(['T%d' % c, 'G%d' % c, 'H%d' % c, 900, 20, 230, 0, 0.15])
+        for nm, f, t, length in (('LHA', 'H', 'A', 20), ('LHB', 'H', 'B', 30), ('LAX', 'A', 'X', 25), ('LBX', 'B', 'X', 15)):
+            lines.append(['%s%d' % (nm, c), '%s%d' % (f, c), '%s%d' % (t, c), length, 100, 230, 'p.u.', 1e-4, 1e-3, 1.75e-3])
+        lines.append(['TIE%d' % c, 'X%d' % c, 'H%d' % ((c + 1) % n), 40, 100, 230, 'p.u.', 1e-4, 1e-3, 1.75e-3])
+        if n > ring_stride:
+            lines.append(['MESH%d' % c, 'X%d' % c, 'X%d' % ((c + ring_stride) % n), 60, 100, 230, 'p.u.', 1e-4, 1e-3, 1.75e-3])
+        # alternate heavier / lighter cells so power actually flows over the ties
+        heavy = (c % 2 == 0)
+        loads.append(['LA%d' % c, 'A%d' % c, 375.0 if heavy else 295.0, 60.0, 'Z'])
+        loads.append(['LB%d' % c, 'B%d' % c, 335.0 if heavy else 315.0, 50.0, 'Z'])
+        gens.append(['M%d' % c, 'G%d' % c, 900, 20, 690.0 if heavy else 640.0, 1.02 if heavy else 1.01, 6.5 if heavy else 6.175, 0,
+                     1.8, 1.7, 0.3, 0.55, 0.25, 0.25, 8.0, 0.4, 0.03, 0.05])
+    return {
+        'base_mva': 900, 'f': 50, 'slack_bus': 'G0', 'base_voltage': 230,
+        'busses': [['name', 'V_n']] + busses,
+        'lines': [['name', 'from_bus', 'to_bus', 'length', 'S_n', 'V_n', 'unit', 'R', 'X', 'B']] + lines,
+        'transformers': [['name', 'from_bus', 'to_bus', 'S_n', 'V_n_from', 'V_n_to', 'R', 'X']] + trafos,
+        'loads': [['name', 'bus', 'P', 'Q', 'model']] + loads,
+        'generators': {'GEN': [['name', 'bus', 'S_n', 'V_n', 'P', 'V', 'H', 'D', 'X_d', 'X_q', 'X_d_t', 'X_q_t', 'X_d_st',
+                                'X_q_st', 'T_d0_t', 'T_q0_t', 'T_d0_st', 'T_q0_st']] + gens},
+        'gov': {'TGOV1': [['name', 'gen', 'R', 'D_t', 'V_min', 'V_max', 'T_1', 'T_2', 'T_3']] +
+                          [['GOV%d' % c, 'M%d' % c, 0.05, 0.02, 0, 1, 0.5, 1, 2] for c in range(n)]},
+        'avr': {'SEXS': [['name', 'gen', 'K', 'T_a', 'T_b', 'T_e', 'E_min', 'E_max']] +
+                         [['AVR%d' % c, 'M%d' % c, 100, 2.0, 10.0, 0.1, -3, 3] for c in range(n)]},
+        'pss': {'STAB1': [['name', 'gen', 'K', 'T', 'T_1', 'T_2', 'T_3', 'T_4', 'H_lim']] +
+                          [['PSS%d' % c, 'M%d' % c, 50, 10.0, 0.5, 0.5, 0.05, 0.05, 0.03] for c in range(n)]},
+    }

@@ -145,8 +145,8 @@ def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
     step_cfg, cfg_sets = event_schedule(sim.time, sim.sc_events)
     obs_bus, chans, rows = observed_rows(init, channel_keys)
     G = len(init.gens)
-    if G > engine.MAX_G:
-        raise engine.EngineError('%d generators: the register-resident stepper handles up to %d' % (G, engine.MAX_G))
+    if G > engine.MAX_GW:
+        raise engine.EngineError('%d generators: the stepper handles up to %d' % (G, engine.MAX_GW))
     m_max = max(len(s) for s in cfg_sets)
     topo = {
         'n_gen': G, 'solver': engine.SOLVER_ID[solver_name], 'n_steps': len(sim.time), 'dt': float(sim.time_step),

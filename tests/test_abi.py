@@ -37,9 +37,16 @@ def test_plan_validation_errors_are_reported():
         engine.Plan(bad)
     with pytest.raises(engine.EngineError, match='duplicates'):
         engine.Plan(dict(topo, rec=[(0, 1, 0), (0, 1, 0)]))
-    with pytest.raises(engine.EngineError, match='register-resident'):
-        engine.Plan(dict(topo, n_gen=40, ctrl=[0] * 40, slot_vary=[-1] * (40 * engine.N_SLOTS), n_obs=40, z_rows=40,
-                         z_cols=40))
+    # 17..128 generators select the wide stepper; more are rejected, and so are the things the wide stepper cannot do
+    wide = dict(topo, n_gen=40, ctrl=[0] * 40, slot_vary=[-1] * (40 * engine.N_SLOTS), n_obs=40, z_rows=40, z_cols=40)
+    assert engine.Plan(wide).handle
+    with pytest.raises(engine.EngineError, match='stepper limit'):
+        engine.Plan(dict(topo, n_gen=200, ctrl=[0] * 200, slot_vary=[-1] * (200 * engine.N_SLOTS), n_obs=200, z_rows=200,
+                         z_cols=200))
+    with pytest.raises(engine.EngineError, match='shared by the batch'):
+        engine.Plan(dict(wide, z_per_sim=1))
+    with pytest.raises(engine.EngineError, match='adjoint is not available'):
+        engine.Plan(dict(wide, ckpt_stride=8))
     with pytest.raises(engine.EngineError, match='n_cfg'):
         engine.Plan(dict(topo, step_cfg=[0, 3, 0, 0]))
     ck = engine.Plan(dict(topo, ckpt_stride=3))

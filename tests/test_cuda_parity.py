@@ -179,3 +179,85 @@ def test_device_math():
     assert ulps(out[2], a / b, 1e-300).max() <= 1.0
     assert ulps(out[3], np.sqrt(np.abs(a)), 1e-300).max() <= 1.0
     assert ulps(out[4], 1.0 / b).max() <= 1.0
+
+
+def _ieee39_sim(P, rows_params, device='cuda', T=2000):
+    from diffpssi_b200 import grids
+    sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver='heun', grid_data=grids.ieee39(), verbose=False,
+              device=device)
+    sim.add_sc_event(1.0, 1.1, 'B16')
+    helpers.apply_overrides(sim, rows_params)
+    sim.set_record_channels(['G%d.omega' % i for i in range(1, 11)])
+    return sim
+
+
+def test_full_size_ieee39_65536():
+    """BASELINE config 3 at full size (65 536 trajectories, 2000 Heun steps): 32 distinct parameter rows tiled 2048 times.
+    Size-independent properties: every tile is bit-identical to the first (rows are independent, no cross-talk, no
+    tail/indexing error anywhere in the batch) and the first tile equals a 32-trajectory run, which in turn matches the
+    C oracle on the same inputs to 1e-9."""
+    from diffpssi_b200 import grids
+    rng = np.random.RandomState(5)
+    n, tile = 32, 2048
+    small = {}
+    for g, (h, xdt) in grids.GENERATOR_NOMINALS['ieee39'].items():
+        small[(g, 'h')] = h * rng.uniform(0.8, 1.25, n)
+        small[(g, 'd')] = rng.uniform(0.0, 2.0, n)
+        small[(g, 'x_d_t')] = xdt * rng.uniform(0.9, 1.1, n)
+    big = {k: np.tile(v, tile) for k, v in small.items()}
+    sim_big = _ieee39_sim(n * tile, big)
+    _, res_big = sim_big.run()
+    assert tuple(res_big.shape) == (n * tile, 2000, 10) and bool(torch.isfinite(res_big).all())
+    first = res_big[:n]
+    for t in (1, 777, tile - 1):
+        assert torch.equal(res_big[t * n:(t + 1) * n], first)
+    chk = res_big.reshape(tile, n, 2000, 10)
+    assert torch.equal(chk.amax(dim=0), chk.amin(dim=0))                 # all 2048 tiles identical, everywhere
+    sim_small = _ieee39_sim(n, small)
+    _, res_small = sim_small.run()
+    assert torch.equal(res_small, first)
+    ref = helpers.run_oracle_for(sim_small, sim_small.last_init, rec_channels=[(0, g, 0) for g in range(10)], full=False)
+    want = ref['rec'].transpose(2, 1, 0)
+    assert np.abs(res_small.cpu().numpy() - want).max() < TOL
+
+
+def test_full_size_k2a_4096():
+    """BASELINE config 2 (K2A, 4096 trajectories, 2000 Heun steps, per-sim H/D/X_d' in the stable range): 24 sampled
+    rows re-run as a small batch are bit-identical, and match the C oracle to 1e-9."""
+    rng = np.random.RandomState(6)
+    P = 4096
+    g = helpers.load_grid('k2a')
+    ov = _random_overrides('k2a', P, rng, 0.9, 1.1)
+
+    def build(Pn, params):
+        s = Pss(parallel_sims=Pn, sim_time=10, time_step=0.005, solver='heun', grid_data=g, verbose=False)
+        s.add_sc_event(1, 1.1, 'B1')
+        helpers.apply_overrides(s, params)
+        s.set_record_channels(['G%d.%s' % (i, f) for f in ('delta', 'omega', 'e_q_st', 'e_d_st') for i in (1, 2, 3, 4)])
+        return s
+
+    big = build(P, ov)
+    _, res = big.run()
+    assert bool(torch.isfinite(res).all())
+    rows = np.sort(rng.choice(P, 24, replace=False))
+    small = build(24, {k: v[rows] for k, v in ov.items()})
+    _, res_s = small.run()
+    assert torch.equal(res[torch.from_numpy(rows).cuda()], res_s)
+    names = [('G%d' % i, f) for f in ('delta', 'omega', 'e_q_st', 'e_d_st') for i in (1, 2, 3, 4)]
+    rec = [(0, int(n_[0][1]) - 1, helpers.oracle.FIELD_NAMES.index(n_[1])) for n_ in names]
+    ref = helpers.run_oracle_for(small, small.last_init, rec_channels=rec, full=False)
+    assert np.abs(res_s.cpu().numpy() - ref['rec'].transpose(2, 1, 0)).max() < TOL
+
+
+@pytest.mark.parametrize('n_cells,P,T,solver', [(20, 37, 60, 'rk4'), (40, 9, 40, 'heun'), (100, 6, 30, 'rk4')])
+def test_wide_stepper_tiled_grid(n_cells, P, T, solver):
+    """BASELINE config 5 family: tiled 5-bus cells with all controllers, 17..128 generators (dps_step_wide_kernel), RK4 /
+    Heun, per-sim H and X_d', a fault at a load bus, recorded generator and load-bus quantities -- vs the C oracle
+    (full n x n complex network, two dense inversions per active fault step) on the same inputs."""
+    from tests.test_host_pipeline import _tiled_case
+    sim, rec = _tiled_case(n_cells, P, T, solver, 'cuda')
+    _, res = sim.run()
+    info = sim.last_plan.info()
+    assert info['g_template'] == n_cells and info['block_threads'] == 512
+    ref = helpers.run_oracle_for(sim, sim.last_init, rec_channels=rec, full=False)
+    assert np.abs(res.cpu().numpy() - ref['rec'].transpose(2, 1, 0)).max() < TOL

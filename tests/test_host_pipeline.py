@@ -104,3 +104,32 @@ def test_backend_argument():
         Pss(parallel_sims=1, sim_time=1, time_step=0.005, solver='heun', backend='numpy')
     with pytest.raises(KeyError):
         Pss(parallel_sims=1, sim_time=1, time_step=0.005, solver='dopri5')
+
+
+def _tiled_case(n_cells, P, T, solver, device):
+    from diffpssi_b200 import grids
+    sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver=solver, grid_data=grids.tiled(n_cells),
+              verbose=False, device=device)
+    sim.add_sc_event(0.05, 0.06, 'A3')                     # fault at a load bus, two active steps
+    rng = np.random.RandomState(0)
+    ov = {}
+    for c in range(n_cells):
+        ov[('M%d' % c, 'h')] = (6.5 if c % 2 == 0 else 6.175) * rng.uniform(0.9, 1.1, P)
+        ov[('M%d' % c, 'x_d_t')] = 0.3 * rng.uniform(0.9, 1.1, P)
+    helpers.apply_overrides(sim, ov)
+    names = ['M%d.omega' % c for c in range(n_cells)] + ['M%d.e_fd' % c for c in range(0, n_cells, 7)] + \
+        ['bus:A3.v_re', 'bus:X5.v_im']
+    rec = [(0, c, 0) for c in range(n_cells)] + [(0, c, 18) for c in range(0, n_cells, 7)] + \
+        [(1, sim.bus_idxs['A3'], 0), (2, sim.bus_idxs['X5'], 0)]
+    sim.set_record_channels(names)
+    return sim, rec
+
+
+def test_tiled_grid_host_pipeline_against_oracle():
+    """Config-5 style tiled grid (here 20 cells = 100 buses / 20 generators: the wide-stepper regime, > 16 generators):
+    prologue + planning + host build of the device code vs the C oracle on the same inputs."""
+    from oracle import adapter
+    sim, rec = _tiled_case(20, 3, 40, 'rk4', 'cpu')
+    res, info = helpers.run_emulated(sim)
+    ref = adapter.run_oracle_for(sim, info['init'], rec_channels=rec, full=False)
+    assert np.abs(res - ref['rec'].transpose(2, 1, 0)).max() < 1e-9
