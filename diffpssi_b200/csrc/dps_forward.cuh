@@ -39,11 +39,13 @@ struct FwdCfg {
     static constexpr int WARPS = 4;                // warps are independent; the block size only sets the launch geometry
     static constexpr int THREADS = 32 * WARPS;
 #ifndef DPS_MIN_BLOCKS
-#define DPS_MIN_BLOCKS 4
+#define DPS_MIN_BLOCKS 3
 #endif
-    static constexpr int MIN_BLOCKS = DPS_MIN_BLOCKS;   // 4 -> 16 warps/SM at <= 128 registers (measured best, profiles/)
-    // a batch-shared Z row also lives in registers while it is small; larger systems read it from shared memory
-    static constexpr bool Z_SMEM = (G > 10);
+    // 3 blocks -> 12 warps/SM at <= 168 registers: no spills.  (4 blocks / 128 registers with the Z row in registers was
+    // 4 % faster but spilled ~200 B per thread, which doubled the kernel's DRAM traffic -- profiles/ncu_r1l_*.)
+    static constexpr int MIN_BLOCKS = DPS_MIN_BLOCKS;
+    // a batch-shared Z lives in shared memory (transposed); only a per-trajectory Z row is held in registers
+    static constexpr bool Z_SMEM = true;
     static constexpr int UPS = DPS_N_SLOTS + 1;    // row stride of the constant table: odd -> conflict-free per-lane rows
 };
 
@@ -197,7 +199,7 @@ dps_step_kernel(const FwdParams p) {
             const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
 #pragma unroll
             for (int k = 0; k < 7; ++k)
-                if (rec_mask & (1u << (DPS_N_STATES + k))) out[ch[DPS_N_STATES + k] * cs] = av[k];
+                if (rec_mask & (1u << (DPS_N_STATES + k))) __stcs(out + ch[DPS_N_STATES + k] * cs, av[k]);
         }
         // extra observed buses (recorded voltages of non-generator buses): last stage only.  Every lane runs the same
         // number of iterations because the shuffles need the whole warp.
@@ -217,8 +219,8 @@ dps_step_kernel(const FwdParams p) {
                 }
                 if (valid) {
                     const int e = rr - p.n_gen;
-                    if (p.obs_chan[e][0] >= 0) p.rec[((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim] = br;
-                    if (p.obs_chan[e][1] >= 0) p.rec[((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim] = bi;
+                    if (p.obs_chan[e][0] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim, br);
+                    if (p.obs_chan[e][1] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim, bi);
                 }
             }
         }
@@ -272,7 +274,8 @@ dps_step_kernel(const FwdParams p) {
             for (int k = 0; k < NS; ++k) x[k] = x[k] + ((acc[k] + f[k]) * dt) / 6.0;
         }
 
-        // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim].  Fields are tested in groups of
+        // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim], written with streaming (evict-first)
+        // stores so the 10 GB output stream does not push the kernel's small working set out of L2.  Fields are tested in groups of
         // four so an all-clear group costs one branch.  (Algebraics were stored by the last stage evaluation.)
         if (rec_mask & 0x1FFFu) {
             const short* ch = p.rec_chan[g];
@@ -283,7 +286,7 @@ dps_step_kernel(const FwdParams p) {
                 if (rec_mask & (0xFu << grp4) & 0x1FFFu) {
 #pragma unroll
                     for (int k = grp4; k < grp4 + 4 && k < DPS_N_STATES; ++k)
-                        if (rec_mask & (1u << k)) out[ch[k] * cs] = (k < NS) ? x[k < NS ? k : 0] : 0.0;
+                        if (rec_mask & (1u << k)) __stcs(out + ch[k] * cs, (k < NS) ? x[k < NS ? k : 0] : 0.0);
                 }
             }
         }

@@ -11,7 +11,7 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_ou
 tail -c 1500 gpurun_out/bench_${TAG}.json
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
 if [ "${LAUNCHES:-0}" = "1" ]; then
-  $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+  $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dps_ -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 fi
 $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dps_step_kernel -s 1 -c 1 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
