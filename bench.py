@@ -273,6 +273,15 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    # DRAM traffic of the dominant kernel, per launch, from the committed ncu capture of this very configuration
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            tj = json.load(f)
+        if P_total == P_GLOBAL and world == 1:
+            traffic = tj['dram_bytes_per_launch']
+    except Exception:
+        pass
     rec_gbs = REC_BYTES_PER_SIM_STEP * P * T_STEPS / (kernel_ms * 1e-3) / 1e9
 
     # ---------------- end-to-end arm: public API with host buffers ----------------------------------------------------
@@ -325,8 +334,9 @@ def main():
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(P_total, world),
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / peak_tf, 'traffic': None,
-                         'kernel': 'dps_step_kernel<10,ctrl,vary>', 'kernel_ms': kernel_ms,
+                         'frac': achieved_tf / peak_tf, 'traffic': traffic,
+                         'kernel': 'dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun>',
+                         'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': REC_BYTES_PER_SIM_STEP * P * T_STEPS,
                          'flops_per_sim_step': FLOPS_PER_SIM_STEP,
                          'peak_source': 'DFMA probe (dps_fp64_peak_probe) in this process; MEASURED_PEAKS.json has no fp64 entry',
                          'hbm': {'achieved': rec_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': rec_gbs / hbm_peak,
