@@ -261,6 +261,9 @@ def main():
     ms_per_step = total_ms / args.steps
     value = P_total * T_STEPS / (ms_per_step * 1e-3)
     finite = float(torch.isfinite(rec).double().mean())
+    # cheap fingerprint of the result (kernel A/B runs must reproduce it): steps 500, 1000, 1999 of every channel
+    probe = rec[:, [500, 1000, T_STEPS - 1], :]
+    checksum = float(torch.where(torch.isfinite(probe), probe, torch.zeros_like(probe)).abs().sum())
     info = prep.plan.info()
 
     # fp64 roofline denominator, measured here (MEASURED_PEAKS.json has no fp64 entry)
@@ -343,7 +346,7 @@ def main():
                                  'bytes_per_sim_step': REC_BYTES_PER_SIM_STEP}},
             'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': 2 * args.steps,
-            'kernel': info, 'finite_fraction': finite, 'clocks': clocks,
+            'kernel': info, 'finite_fraction': finite, 'checksum': checksum, 'clocks': clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -143,6 +143,18 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
             set_error("dps_plan_create: recorder channel %d has unknown kind %d", c, ch.kind); delete pl; return 1;
         }
     }
+    if (!wide) {
+        // regular recorder layout?  (same field set for every generator, channel = base[field] + generator)
+        bool regular = t->n_rec > 0;
+        for (int g = 1; g < t->n_gen && regular; ++g) regular = (b.rec_mask[g] == b.rec_mask[0]);
+        for (int k = 0; k < DPS_N_FIELDS && regular; ++k) {
+            if (!(b.rec_mask[0] & (1u << k))) continue;
+            for (int g = 0; g < t->n_gen && regular; ++g) regular = (b.rec_chan[g][k] == b.rec_chan[0][k] + g);
+            b.rec_fbase[k] = b.rec_chan[0][k];
+        }
+        b.rec_regular = regular ? 1 : 0;
+        b.rec_umask = regular ? b.rec_mask[0] : 0u;
+    }
     *out = pl;
     return 0;
 }

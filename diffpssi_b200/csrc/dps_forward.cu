@@ -19,11 +19,14 @@ int fwd_template_g(int n_gen) {
 }
 
 void fwd_geometry(int g_template, int* threads, int* sims_per_block) {
-    *threads = 128;
-    *sims_per_block = 4 * (32 / g_template);
+    *threads = 32 * DPS_FWD_WARPS;
+    *sims_per_block = DPS_FWD_WARPS * (32 / g_template);
 }
 
 cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream, int* regs) {
+#ifdef DPS_ONLY_G10      // kernel A/B experiment builds (tools/build_variant.sh): only the bench specialisation is linked
+    return g_template == 10 ? launch_forward_g<10>(p, cmask, pmode, stream, regs) : cudaErrorInvalidValue;
+#else
     switch (g_template) {
         case 1: return launch_forward_g<1>(p, cmask, pmode, stream, regs);
         case 2: return launch_forward_g<2>(p, cmask, pmode, stream, regs);
@@ -36,6 +39,7 @@ cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pm
         case 16: return launch_forward_g<16>(p, cmask, pmode, stream, regs);
         default: return cudaErrorInvalidValue;
     }
+#endif
 }
 
 }  // namespace dps

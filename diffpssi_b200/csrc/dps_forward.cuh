@@ -36,10 +36,10 @@ namespace dps {
 template <int G>
 struct FwdCfg {
     static constexpr int SPW = 32 / G;             // trajectories per warp
-    static constexpr int WARPS = 4;                // warps are independent; the block size only sets the launch geometry
+    static constexpr int WARPS = DPS_FWD_WARPS;    // warps are independent; the block size only sets the launch geometry
     static constexpr int THREADS = 32 * WARPS;
 #ifndef DPS_MIN_BLOCKS
-#define DPS_MIN_BLOCKS 3
+#define DPS_MIN_BLOCKS (12 / DPS_FWD_WARPS)
 #endif
     // 3 blocks -> 12 warps/SM at <= 168 registers: no spills.  (4 blocks / 128 registers with the Z row in registers was
     // 4 % faster but spilled ~200 B per thread, which doubled the kernel's DRAM traffic -- profiles/ncu_r1l_*.)
@@ -80,6 +80,9 @@ dps_step_kernel(const FwdParams p) {
         s_upar[gi * UPS + k] = ok ? p.upar[i] : 0.0;
         if (PMODE == 2) s_vary[i] = ok ? p.slot_vary[i] : (short)-1;
     }
+    // exchange lines start at zero and only live generator lanes ever store, so the slots of padding lanes
+    // (template G > n_gen) contribute exactly 0 to V = Z I without a per-stage select
+    for (int i = threadIdx.x; i < C::WARPS * 64; i += blockDim.x) s_cur[i] = make_double2(0.0, 0.0);
     if (ZPS == 0) {
         for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
             const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
@@ -146,6 +149,11 @@ dps_step_kernel(const FwdParams p) {
 
     const double dt = p.dt, hdt = 0.5 * p.dt;
     const unsigned rec_mask = live ? p.rec_mask[g] : 0u;
+    // regular recorder layout (dps_internal.h): launch-uniform field mask, channel = rec_fbase[field] + generator
+    const bool rec_regular = p.rec_regular != 0;
+    const unsigned rec_umask = p.rec_umask;
+    const long long rec_cs = (long long)p.n_steps * P;                 // channel stride
+    double* const rec_thread = p.rec + (long long)g * rec_cs + sim;    // channel g, step 0, this trajectory
     const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
     int step = p.step_begin;
     int buf = 0;
@@ -162,12 +170,11 @@ dps_step_kernel(const FwdParams p) {
         if (PMODE == 3) injection(X, par_const, sd, cd, i_re, i_im);
         else if (PMODE == 1) injection(X, par_fast, sd, cd, i_re, i_im);
         else injection(X, par_gen, sd, cd, i_re, i_im);
-        if (!gen_live) { i_re = 0.0; i_im = 0.0; }
         // exchange inside the warp through its private, double-buffered shared-memory line: one STS.128, then every
         // lane reads the G currents of its own trajectory as broadcast LDS.128 (a quarter of the wavefronts the
         // equivalent 4*G 32-bit shuffles cost); __syncwarp orders the store against the loads.
         double2* cw = cur_w + buf * 32;
-        cw[lane] = make_double2(i_re, i_im);
+        if (gen_live) cw[lane] = make_double2(i_re, i_im);
         __syncwarp();
         buf ^= 1;
         const double2* cgrp = cw + base;
@@ -187,12 +194,22 @@ dps_step_kernel(const FwdParams p) {
             vib = fma(zim, jr, vib);
         }
         const double v_re = vra + vrb, v_im = via + vib;
-        if (PMODE == 3) stage_derivatives<CTRL>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
-        else if (PMODE == 1) stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
-        else stage_derivatives<CTRL>(X, par_gen, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        if (PMODE == 3) stage_derivatives<CTRL, true>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        else if (PMODE == 1) stage_derivatives<CTRL, true>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        else stage_derivatives<CTRL, true>(X, par_gen, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
 
         // recorded algebraics hold the values of the LAST stage evaluation of the step (simulator.py:540-543)
-        if (last_stage && (rec_mask >> DPS_N_STATES)) {
+        if (last_stage && rec_regular) {
+            if (rec_umask >> DPS_N_STATES) {       // uniform test; stores predicated on `live` only
+                double* out = rec_thread + (long long)step * P;
+                const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (rec_umask & (1u << (DPS_N_STATES + k))) {
+                        if (live) __stcs(out + (long long)p.rec_fbase[DPS_N_STATES + k] * rec_cs, av[k]);
+                    }
+            }
+        } else if (last_stage && (rec_mask >> DPS_N_STATES)) {
             const short* ch = p.rec_chan[g];
             double* out = p.rec + (long long)step * P + sim;
             const long long cs = (long long)p.n_steps * P;
@@ -277,7 +294,25 @@ dps_step_kernel(const FwdParams p) {
         // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim], written with streaming (evict-first)
         // stores so the 10 GB output stream does not push the kernel's small working set out of L2.  Fields are tested in groups of
         // four so an all-clear group costs one branch.  (Algebraics were stored by the last stage evaluation.)
-        if (rec_mask & 0x1FFFu) {
+        if (rec_regular) {
+            if (rec_umask & 0x1FFFu) {
+                double* out = rec_thread + (long long)step * P;
+#pragma unroll
+                for (int grp4 = 0; grp4 < NS; grp4 += 4) {           // uniform tests in groups of four fields
+                    if (rec_umask & (0xFu << grp4)) {
+#pragma unroll
+                        for (int k = grp4; k < grp4 + 4 && k < NS; ++k)
+                            if (rec_umask & (1u << k)) {
+                                if (live) __stcs(out + (long long)p.rec_fbase[k] * rec_cs, x[k]);
+                            }
+                    }
+                }
+                if (NS < DPS_N_STATES) {
+                    for (int k = NS; k < DPS_N_STATES; ++k)
+                        if ((rec_umask & (1u << k)) && live) __stcs(out + (long long)p.rec_fbase[k] * rec_cs, 0.0);
+                }
+            }
+        } else if (rec_mask & 0x1FFFu) {
             const short* ch = p.rec_chan[g];
             double* out = p.rec + (long long)step * P + sim;
             const long long cs = (long long)p.n_steps * P;

@@ -8,6 +8,9 @@
 
 namespace dps {
 
+#ifndef DPS_FWD_WARPS
+#define DPS_FWD_WARPS 4               // warps per block of the warp-exchange stepper (12 resident warps per SM)
+#endif
 constexpr int MAX_G = 16;            // generators handled by the warp-exchange stepper (dps_forward.cuh)
 constexpr int MAX_GW = 128;          // generators handled by the wide stepper (dps_forward_wide.cuh)
 constexpr int MAX_SEG = 48;          // network-configuration change points per launch
@@ -34,6 +37,11 @@ struct FwdParams {
     short obs_chan[MAX_EXTRA_OBS][2];       // channel of (re, im) of extra observed row e, or -1
     short slot_vary[MAX_G * DPS_N_SLOTS];   // row of vpar or -1
     double cpar[DPS_N_SLOTS];               // PMODE 3: controller constants common to all generators
+    // "regular" recorder: every generator records the same fields (rec_umask) and field k of generator g is channel
+    // rec_fbase[k] + g.  The stepper then needs no per-thread channel lookup and no divergent branch per store.
+    int rec_regular;
+    unsigned rec_umask;
+    short rec_fbase[DPS_N_FIELDS];
 };
 
 // Parameter block of the wide stepper: same scalars, tables sized for MAX_GW generators (~11 KB, passed by value).

@@ -53,7 +53,18 @@ __device__ __forceinline__ double dps_sqrt(double s) {
     y = fma(y, e, y);
     const double r = s * y;
     const double res = fma(fma(-r, r, s), 0.5 * y, r);
-    return (s > 0.0) ? res : 0.0;
+    // s is a sum of squares: an integer test of its high word (normal and positive) replaces the FP64 compare
+    return (__double2hiint(s) >= 0x00100000) ? res : 0.0;
+}
+// sqrt of a strictly positive normal number: no zero guard (the caller adds a 1e-300 floor for free inside an FMA)
+__device__ __forceinline__ double dps_sqrt_pos(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double h = 0.5 * y;
+    const double e = fma(-s * y, h, 0.5);
+    y = fma(y, e, y);
+    const double r = s * y;
+    return fma(fma(-r, r, s), 0.5 * y, r);
 }
 // sin/cos with 2-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4].
 // Rotor angles stay far below the 1e6 rad where the 2-term reduction starts to lose bits.
@@ -77,17 +88,17 @@ __device__ __forceinline__ void dps_sincos(double x, double* sp, double* cp) {
     pc = fma(z, pc, C[14]);
     pc = fma(z, pc, C[15]);
     const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-    double s = (q & 1) ? cr : sr;
-    double c = (q & 1) ? sr : cr;
-    if (q & 2) s = -s;
-    if ((q + 1) & 2) c = -c;
-    *sp = s;
-    *cp = c;
+    const double s = (q & 1) ? cr : sr;
+    const double c = (q & 1) ? sr : cr;
+    // quadrant signs are XORed into the high words (integer pipe) instead of FP64 negations
+    *sp = __hiloint2double(__double2hiint(s) ^ ((q & 2) << 30), __double2loint(s));
+    *cp = __hiloint2double(__double2hiint(c) ^ (((q + 1) & 2) << 30), __double2loint(c));
 }
 #else
 inline double dps_rcp(double x) { return 1.0 / x; }
 inline double dps_div(double a, double b) { return a / b; }
 inline double dps_sqrt(double s) { return sqrt(s); }
+inline double dps_sqrt_pos(double s) { return sqrt(s); }
 inline void dps_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 #endif
 
@@ -191,7 +202,12 @@ __device__ __forceinline__ double windup_gate(double state, double dx, double lo
 // One stage for one generator, given its bus voltage (v_re, v_im): update_internal_vars
 // (synchronous_machine.py:271-277) + differential() (synchronous_machine.py:148-172) with the controller
 // get_output()/differential() pairs it calls.  Writes f[0..12] (zero for absent controllers).
-template <bool CTRL, class PR>
+//
+// VOTE (device only; the caller guarantees that all 32 lanes of the warp are in the call): the limiter / anti-windup
+// selects are skipped when NO lane of the warp sits at a limit -- the common case outside fault transients.  The five
+// "at a limit" tests depend on states only; one warp vote then guards the select blocks with warp-uniform branches.
+// Results are identical either way: a block that is inside its limits passes its input through unchanged.
+template <bool CTRL, bool VOTE = false, class PR>
 __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par, int ctrl, double fn,
                                                   double sd, double cd, double v_re, double v_im,
                                                   double* f, Algebraics& alg) {
@@ -215,7 +231,9 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
     for (int k = 6; k < DPS_N_STATES; ++k) f[k] = 0.0;
 
     if (CTRL) {
-        double v_pss = 0.0;
+        // ---- linear part of the stabiliser and the "at a limit" tests (functions of the states only) -------------
+        double o2 = 0.0, hl = 0.0;
+        bool at_limit = false;
         if (ctrl & DPS_CTRL_PSS) {
             // STAB1.get_output is only called when an exciter exists (synchronous_machine.py:148-150); without
             // one the block inputs keep their initial 0 and only the decay terms remain.
@@ -226,38 +244,64 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
             const double in1 = fed ? w : 0.0;
             const double o1 = par(DPS_S_S_R1) * in1 + par(DPS_S_S_OMR1) * x1;        // blocks.py:319
             const double in2 = fed ? o1 : 0.0;
-            const double o2 = par(DPS_S_S_R2) * in2 + par(DPS_S_S_OMR2) * x2;
+            o2 = par(DPS_S_S_R2) * in2 + par(DPS_S_S_OMR2) * x2;
             f[DPS_X_PSS_W] = w;
             f[DPS_X_PSS_LL1] = par(DPS_S_S_INV_T3) * (in1 - x1);                     // blocks.py:290
             f[DPS_X_PSS_LL2] = par(DPS_S_S_INV_T4) * (in2 - x2);
-            const double hl = par(DPS_S_S_HLIM);
-            v_pss = clampd(o2, -hl, hl);                                             // blocks.py:241
+            hl = par(DPS_S_S_HLIM);
+            if (VOTE) at_limit = (o2 < -hl) || (o2 > hl);
+        }
+        double xe = 0.0, emin = 0.0, emax = 0.0, xg = 0.0, vmin = 0.0, vmax = 0.0;
+        if (ctrl & DPS_CTRL_AVR) {
+            xe = x[DPS_X_AVR_PT1]; emin = par(DPS_S_A_EMIN); emax = par(DPS_S_A_EMAX);
+            if (VOTE) at_limit = at_limit || (xe <= emin) || (xe >= emax);
+        }
+        if (ctrl & DPS_CTRL_GOV) {
+            xg = x[DPS_X_GOV_PT1]; vmin = par(DPS_S_G_VMIN); vmax = par(DPS_S_G_VMAX);
+            if (VOTE) at_limit = at_limit || (xg <= vmin) || (xg >= vmax);
+        }
+#ifdef __CUDA_ARCH__
+        const bool limiting = VOTE ? (__any_sync(0xffffffffu, at_limit) != 0) : true;
+#else
+        const bool limiting = true;
+#endif
+        double v_pss = 0.0;
+        if (ctrl & DPS_CTRL_PSS) {
+            v_pss = o2;
+            if (limiting) v_pss = clampd(o2, -hl, hl);                               // blocks.py:241
         }
         if (ctrl & DPS_CTRL_AVR) {
             // SEXS.get_output(|v_bb| - v_pss), exciters.py:111-114
-            const double v_abs = dps_sqrt(v_re * v_re + v_im * v_im);
+            // |v|: the 1e-300 floor (far below one ulp of any |v|^2 > 1e-284) replaces the zero guard of the root
+            const double v_abs = dps_sqrt_pos(fma(v_re, v_re, fma(v_im, v_im, 1e-300)));
             const double sig = (ctrl & DPS_CTRL_PSS) ? (v_abs - v_pss) : v_abs;
             const double u = (par(DPS_S_A_VSET) - sig) + par(DPS_S_A_BIAS);
-            const double xll = x[DPS_X_AVR_LL], xe = x[DPS_X_AVR_PT1];
+            const double xll = x[DPS_X_AVR_LL];
             const double o = par(DPS_S_A_R) * u + par(DPS_S_A_OMR) * xll;
-            const double emin = par(DPS_S_A_EMIN), emax = par(DPS_S_A_EMAX);
-            const Pt1Lim lim(xe, emin, emax);
-            e_fd = lim.out;
             f[DPS_X_AVR_LL] = par(DPS_S_A_INV_TB) * (u - xll);
             const double dxe = par(DPS_S_A_INV_TE) * (par(DPS_S_A_K) * o - xe);      // blocks.py:143
-            f[DPS_X_AVR_PT1] = lim.gate(dxe);
+            e_fd = xe;
+            f[DPS_X_AVR_PT1] = dxe;
+            if (limiting) {
+                const Pt1Lim lim(xe, emin, emax);
+                e_fd = lim.out;
+                f[DPS_X_AVR_PT1] = lim.gate(dxe);
+            }
         }
         if (ctrl & DPS_CTRL_GOV) {
             // TGOV1.get_output(omega), governors.py:115-123
             const double u = par(DPS_S_G_PREF) - omega;
-            const double xg = x[DPS_X_GOV_PT1], xll = x[DPS_X_GOV_LL];
-            const double vmin = par(DPS_S_G_VMIN), vmax = par(DPS_S_G_VMAX);
-            const Pt1Lim lim(xg, vmin, vmax);
-            const double gs = lim.out;
+            const double xll = x[DPS_X_GOV_LL];
+            const double dxg = par(DPS_S_G_INV_T1) * (par(DPS_S_G_GAIN) * u - xg);
+            double gs = xg;
+            f[DPS_X_GOV_PT1] = dxg;
+            if (limiting) {
+                const Pt1Lim lim(xg, vmin, vmax);
+                gs = lim.out;
+                f[DPS_X_GOV_PT1] = lim.gate(dxg);
+            }
             const double o = par(DPS_S_G_R) * gs + par(DPS_S_G_OMR) * xll;
             p_m = o - par(DPS_S_G_DT) * omega;
-            const double dxg = par(DPS_S_G_INV_T1) * (par(DPS_S_G_GAIN) * u - xg);
-            f[DPS_X_GOV_PT1] = lim.gate(dxg);
             f[DPS_X_GOV_LL] = par(DPS_S_G_INV_T3) * (gs - xll);
         }
     }
