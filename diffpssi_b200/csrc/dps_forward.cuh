@@ -57,8 +57,13 @@ dps_step_kernel(const FwdParams p) {
     constexpr bool CTRL = (CM != 0);                 // CM: -1 = per-generator controller flags, else the common flag set
     constexpr int NS = CTRL ? DPS_N_STATES : 6;      // live states per generator
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_z = reinterpret_cast<double2*>(smem_raw);                         // ZPS==0: [n_cfg][col j][row g] (re, im)
-    double2* s_cur = s_z + (ZPS == 0 ? p.n_cfg * G * G : 0);                     // [WARPS][2][32] current exchange lines
+    // ZPS==0: Z of every configuration, transposed: [n_cfg][col j][row g], real and imaginary parts in separate planes.
+    // The G lanes of a trajectory read G consecutive doubles (LDS.64: the three trajectory groups of a warp hit the same
+    // addresses, two conflict-free wavefronts per load).  The interleaved (re, im) LDS.128 version of r1m needed 7
+    // wavefronts per load (4 ideal + bank conflicts between the groups) and kept the shared-memory pipe 69 % busy.
+    double* s_zr = reinterpret_cast<double*>(smem_raw);
+    double* s_zi = s_zr + (ZPS == 0 ? p.n_cfg * G * G : 0);
+    double2* s_cur = reinterpret_cast<double2*>(s_zi + (ZPS == 0 ? p.n_cfg * G * G : 0));   // [WARPS][2][32] exchange lines
     double* s_upar = reinterpret_cast<double*>(s_cur + C::WARPS * 64);           // [G][UPS]
     short* s_vary = reinterpret_cast<short*>(s_upar + G * UPS);                  // [G][DPS_N_SLOTS]
 
@@ -88,7 +93,8 @@ dps_step_kernel(const FwdParams p) {
             const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
             const bool ok = row < p.n_gen && col < p.n_gen;
             const double* e = p.zsub + (((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2;
-            s_z[i] = ok ? make_double2(e[0], e[1]) : make_double2(0.0, 0.0);
+            s_zr[i] = ok ? e[0] : 0.0;
+            s_zi[i] = ok ? e[1] : 0.0;
         }
     }
     __syncthreads();
@@ -125,7 +131,7 @@ dps_step_kernel(const FwdParams p) {
     double zr[ZPS ? G : 1], zi[ZPS ? G : 1];
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
-    const double2* zcol = nullptr;                 // ZPS==0: &Zt[cfg][0][gl]; element j at zcol[j*G]
+    const double *zcol_r = nullptr, *zcol_i = nullptr;   // ZPS==0: &Zt[cfg][0][gl]; element j at zcol[j*G]
     auto load_z_row = [&](int cfg) {
         if (ZPS) {
             const double* zbase = p.zsub + (((long long)cfg * p.z_rows + g) * p.z_cols) * 2 * zb + zs;
@@ -136,7 +142,8 @@ dps_step_kernel(const FwdParams p) {
                 zi[ZPS ? j : 0] = ok ? __ldg(zbase + (long long)(2 * j + 1) * zb) : 0.0;
             }
         } else {
-            zcol = s_z + (long long)cfg * G * G + gl;
+            zcol_r = s_zr + cfg * G * G + gl;
+            zcol_i = s_zi + cfg * G * G + gl;
         }
     };
 
@@ -187,7 +194,7 @@ dps_step_kernel(const FwdParams p) {
             const double jr = cj.x, ji = cj.y;
             double zre, zim;
             if (ZPS) { zre = zr[ZPS ? j : 0]; zim = zi[ZPS ? j : 0]; }
-            else { const double2 z = zcol[j * G]; zre = z.x; zim = z.y; }
+            else { zre = zcol_r[j * G]; zim = zcol_i[j * G]; }
             vra = fma(zre, jr, vra);
             vrb = fma(-zim, ji, vrb);
             via = fma(zre, ji, via);

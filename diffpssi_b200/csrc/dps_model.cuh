@@ -58,13 +58,13 @@ __device__ __forceinline__ double dps_sqrt(double s) {
 }
 // sqrt of a strictly positive normal number: no zero guard (the caller adds a 1e-300 floor for free inside an FMA)
 __device__ __forceinline__ double dps_sqrt_pos(double s) {
+    // coupled (Goldschmidt) iteration: g -> sqrt(s), h -> 1/(2 sqrt(s)); five dependent FP64 levels after the MUFU
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    const double h = 0.5 * y;
-    const double e = fma(-s * y, h, 0.5);
-    y = fma(y, e, y);
-    const double r = s * y;
-    return fma(fma(-r, r, s), 0.5 * y, r);
+    const double g = s * y, h = 0.5 * y;
+    const double e = fma(-g, h, 0.5);
+    const double g1 = fma(g, e, g), h1 = fma(h, e, h);
+    return fma(fma(-g1, g1, s), h1, g1);         // residual correction
 }
 // sin/cos with 2-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4].
 // Rotor angles stay far below the 1e6 rad where the 2-term reduction starts to lose bits.
@@ -75,19 +75,16 @@ __device__ __forceinline__ void dps_sincos(double x, double* sp, double* cp) {
     const double k = t - C[1];
     double r = fma(-k, C[2], x);
     r = fma(-k, C[3], r);
+    // Estrin evaluation of the two fdlibm kernel polynomials: three dependent levels instead of Horner's five (the
+    // kernel is bound by FP64 dependency latency, not by the pipe's throughput -- profiles/README.md)
     const double z = r * r;
-    double ps = fma(z, C[4], C[5]);
-    ps = fma(z, ps, C[6]);
-    ps = fma(z, ps, C[7]);
-    ps = fma(z, ps, C[8]);
-    ps = fma(z, ps, C[9]);
+    const double z2 = z * z;
+    const double sa = fma(z, C[4], C[5]), sb = fma(z, C[6], C[7]), sc = fma(z, C[8], C[9]);
+    const double ca = fma(z, C[10], C[11]), cb = fma(z, C[12], C[13]), cc = fma(z, C[14], C[15]);
+    const double ps = fma(fma(sa, z2, sb), z2, sc);
+    const double pc = fma(fma(ca, z2, cb), z2, cc);
     const double sr = fma(z * r, ps, r);
-    double pc = fma(z, C[10], C[11]);
-    pc = fma(z, pc, C[12]);
-    pc = fma(z, pc, C[13]);
-    pc = fma(z, pc, C[14]);
-    pc = fma(z, pc, C[15]);
-    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double cr = fma(z2, pc, fma(z, -0.5, 1.0));
     const double s = (q & 1) ? cr : sr;
     const double c = (q & 1) ? sr : cr;
     // quadrant signs are XORed into the high words (integer pipe) instead of FP64 negations
@@ -203,27 +200,30 @@ __device__ __forceinline__ double windup_gate(double state, double dx, double lo
 // (synchronous_machine.py:271-277) + differential() (synchronous_machine.py:148-172) with the controller
 // get_output()/differential() pairs it calls.  Writes f[0..12] (zero for absent controllers).
 //
-// VOTE (device only; the caller guarantees that all 32 lanes of the warp are in the call): the limiter / anti-windup
-// selects are skipped when NO lane of the warp sits at a limit -- the common case outside fault transients.  The five
-// "at a limit" tests depend on states only; one warp vote then guards the select blocks with warp-uniform branches.
-// Results are identical either way: a block that is inside its limits passes its input through unchanged.
-template <bool CTRL, bool VOTE = false, class PR>
-__device__ __forceinline__ void stage_derivatives(const double* x, const PR& par, int ctrl, double fn,
-                                                  double sd, double cd, double v_re, double v_im,
-                                                  double* f, Algebraics& alg) {
+// LIM = true applies the limiter / anti-windup selects (blocks.py:145-149, 181, 241).  LIM = false is the same code
+// without them, valid when no block sits at a limit (a block inside its limits passes its input through unchanged):
+// stage_derivatives<CTRL, VOTE = true> tests the limits of all 32 lanes with one warp vote (they are functions of the
+// states only) and takes the select-free body when no lane needs them -- the common case outside fault transients.
+// Each body is one straight-line block, so the scheduler can interleave its independent chains freely.
+template <bool CTRL, bool LIM, class PR>
+__device__ __forceinline__ void stage_body(const double* x, const PR& par, int ctrl, double fn,
+                                           double sd, double cd, double v_re, double v_im,
+                                           double* f, Algebraics& alg) {
     const double omega = x[DPS_X_OMEGA];
     const double eqst = x[DPS_X_EQST], edst = x[DPS_X_EDST];
     // e'' = e_q'' e^{j delta} + e_d'' e^{j(delta - pi/2)}                              :273
-    const double e_re = eqst * cd + edst * sd;
-    const double e_im = eqst * sd - edst * cd;
+    // (every multiply-add below is an explicit fma: the LIM / non-LIM instantiations then round identically, so a
+    // trajectory does not depend on which other trajectories share its warp)
+    const double e_re = fma(eqst, cd, edst * sd);
+    const double e_im = fma(eqst, sd, -(edst * cd));
     // i_gen = (e'' - v)/(j x_d'')   (x_d'' on both axes, as the reference)             :275
     const double inv_xdst = par(DPS_S_INV_XDST);
     const double i_re = (e_im - v_im) * inv_xdst;
     const double i_im = -((e_re - v_re) * inv_xdst);
-    const double p_e = v_re * i_re + v_im * i_im;                                    // :274
+    const double p_e = fma(v_re, i_re, v_im * i_im);                                 // :274
     // (i_d + j i_q) = i_gen e^{j(pi/2 - delta)} = i_gen (s + j c)                      :276-277
-    const double i_d = i_re * sd - i_im * cd;
-    const double i_q = i_re * cd + i_im * sd;
+    const double i_d = fma(i_re, sd, -(i_im * cd));
+    const double i_q = fma(i_re, cd, i_im * sd);
 
     double e_fd = par(DPS_S_EFD0);      // held constant without an exciter (synchronous_machine.py:314)
     double p_m = par(DPS_S_PM0);        // held constant without a governor (synchronous_machine.py:313)
@@ -231,40 +231,31 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
     for (int k = 6; k < DPS_N_STATES; ++k) f[k] = 0.0;
 
     if (CTRL) {
-        // ---- linear part of the stabiliser and the "at a limit" tests (functions of the states only) -------------
+        constexpr bool limiting = LIM;
         double o2 = 0.0, hl = 0.0;
-        bool at_limit = false;
         if (ctrl & DPS_CTRL_PSS) {
             // STAB1.get_output is only called when an exciter exists (synchronous_machine.py:148-150); without
             // one the block inputs keep their initial 0 and only the decay terms remain.
             const bool fed = (ctrl & DPS_CTRL_AVR) != 0;
             const double xw = x[DPS_X_PSS_W], x1 = x[DPS_X_PSS_LL1], x2 = x[DPS_X_PSS_LL2];
             // Washout: output == derivative, blocks.py:382, 413
-            const double w = par(DPS_S_S_INV_TW) * (par(DPS_S_S_KW) * (fed ? omega : 0.0) - xw);
+            const double w = par(DPS_S_S_INV_TW) * fma(par(DPS_S_S_KW), (fed ? omega : 0.0), -xw);
             const double in1 = fed ? w : 0.0;
-            const double o1 = par(DPS_S_S_R1) * in1 + par(DPS_S_S_OMR1) * x1;        // blocks.py:319
+            const double o1 = fma(par(DPS_S_S_R1), in1, par(DPS_S_S_OMR1) * x1);     // blocks.py:319
             const double in2 = fed ? o1 : 0.0;
-            o2 = par(DPS_S_S_R2) * in2 + par(DPS_S_S_OMR2) * x2;
+            o2 = fma(par(DPS_S_S_R2), in2, par(DPS_S_S_OMR2) * x2);
             f[DPS_X_PSS_W] = w;
             f[DPS_X_PSS_LL1] = par(DPS_S_S_INV_T3) * (in1 - x1);                     // blocks.py:290
             f[DPS_X_PSS_LL2] = par(DPS_S_S_INV_T4) * (in2 - x2);
             hl = par(DPS_S_S_HLIM);
-            if (VOTE) at_limit = (o2 < -hl) || (o2 > hl);
         }
         double xe = 0.0, emin = 0.0, emax = 0.0, xg = 0.0, vmin = 0.0, vmax = 0.0;
         if (ctrl & DPS_CTRL_AVR) {
             xe = x[DPS_X_AVR_PT1]; emin = par(DPS_S_A_EMIN); emax = par(DPS_S_A_EMAX);
-            if (VOTE) at_limit = at_limit || (xe <= emin) || (xe >= emax);
         }
         if (ctrl & DPS_CTRL_GOV) {
             xg = x[DPS_X_GOV_PT1]; vmin = par(DPS_S_G_VMIN); vmax = par(DPS_S_G_VMAX);
-            if (VOTE) at_limit = at_limit || (xg <= vmin) || (xg >= vmax);
         }
-#ifdef __CUDA_ARCH__
-        const bool limiting = VOTE ? (__any_sync(0xffffffffu, at_limit) != 0) : true;
-#else
-        const bool limiting = true;
-#endif
         double v_pss = 0.0;
         if (ctrl & DPS_CTRL_PSS) {
             v_pss = o2;
@@ -274,12 +265,16 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
             // SEXS.get_output(|v_bb| - v_pss), exciters.py:111-114
             // |v|: the 1e-300 floor (far below one ulp of any |v|^2 > 1e-284) replaces the zero guard of the root
             const double v_abs = dps_sqrt_pos(fma(v_re, v_re, fma(v_im, v_im, 1e-300)));
-            const double sig = (ctrl & DPS_CTRL_PSS) ? (v_abs - v_pss) : v_abs;
-            const double u = (par(DPS_S_A_VSET) - sig) + par(DPS_S_A_BIAS);
+            // u = v_set - (|v| - v_pss) + bias (exciters.py:113), associated so that only ONE addition follows the root:
+            // the set-point terms do not depend on the network solve and are summed while it is in flight
+            const double c0 = (ctrl & DPS_CTRL_PSS) ? ((par(DPS_S_A_VSET) + par(DPS_S_A_BIAS)) + v_pss)
+                                                    : (par(DPS_S_A_VSET) + par(DPS_S_A_BIAS));
             const double xll = x[DPS_X_AVR_LL];
-            const double o = par(DPS_S_A_R) * u + par(DPS_S_A_OMR) * xll;
+            const double oll = par(DPS_S_A_OMR) * xll;
+            const double u = c0 - v_abs;
+            const double o = fma(par(DPS_S_A_R), u, oll);
             f[DPS_X_AVR_LL] = par(DPS_S_A_INV_TB) * (u - xll);
-            const double dxe = par(DPS_S_A_INV_TE) * (par(DPS_S_A_K) * o - xe);      // blocks.py:143
+            const double dxe = par(DPS_S_A_INV_TE) * fma(par(DPS_S_A_K), o, -xe);    // blocks.py:143
             e_fd = xe;
             f[DPS_X_AVR_PT1] = dxe;
             if (limiting) {
@@ -292,7 +287,7 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
             // TGOV1.get_output(omega), governors.py:115-123
             const double u = par(DPS_S_G_PREF) - omega;
             const double xll = x[DPS_X_GOV_LL];
-            const double dxg = par(DPS_S_G_INV_T1) * (par(DPS_S_G_GAIN) * u - xg);
+            const double dxg = par(DPS_S_G_INV_T1) * fma(par(DPS_S_G_GAIN), u, -xg);
             double gs = xg;
             f[DPS_X_GOV_PT1] = dxg;
             if (limiting) {
@@ -300,22 +295,66 @@ __device__ __forceinline__ void stage_derivatives(const double* x, const PR& par
                 gs = lim.out;
                 f[DPS_X_GOV_PT1] = lim.gate(dxg);
             }
-            const double o = par(DPS_S_G_R) * gs + par(DPS_S_G_OMR) * xll;
-            p_m = o - par(DPS_S_G_DT) * omega;
+            const double o = fma(par(DPS_S_G_R), gs, par(DPS_S_G_OMR) * xll);
+            p_m = fma(-par(DPS_S_G_DT), omega, o);
             f[DPS_X_GOV_LL] = par(DPS_S_G_INV_T3) * (gs - xll);
         }
     }
 
     // synchronous_machine.py:158-164
     const double t_m = dps_div(p_m, 1.0 + omega);
-    f[DPS_X_OMEGA] = par(DPS_S_INV_2H) * ((t_m - p_e) - par(DPS_S_D) * omega);
+    f[DPS_X_OMEGA] = par(DPS_S_INV_2H) * (fma(-par(DPS_S_D), omega, t_m) - p_e);    // (t_m - p_e - D omega)/(2H)
     f[DPS_X_DELTA] = omega * ((2.0 * 3.141592653589793) * fn);
-    f[DPS_X_EQT] = par(DPS_S_INV_TD0T) * ((e_fd - x[DPS_X_EQT]) - i_d * par(DPS_S_XD_XDT));
-    f[DPS_X_EDT] = par(DPS_S_INV_TQ0T) * (-x[DPS_X_EDT] + i_q * par(DPS_S_XQ_XQT));
-    f[DPS_X_EQST] = par(DPS_S_INV_TD0ST) * ((x[DPS_X_EQT] - eqst) - i_d * par(DPS_S_XDT_XDST));
-    f[DPS_X_EDST] = par(DPS_S_INV_TQ0ST) * ((x[DPS_X_EDT] - edst) + i_q * par(DPS_S_XQT_XQST));
+    f[DPS_X_EQT] = par(DPS_S_INV_TD0T) * fma(-i_d, par(DPS_S_XD_XDT), e_fd - x[DPS_X_EQT]);
+    f[DPS_X_EDT] = par(DPS_S_INV_TQ0T) * fma(i_q, par(DPS_S_XQ_XQT), -x[DPS_X_EDT]);
+    f[DPS_X_EQST] = par(DPS_S_INV_TD0ST) * fma(-i_d, par(DPS_S_XDT_XDST), x[DPS_X_EQT] - eqst);
+    f[DPS_X_EDST] = par(DPS_S_INV_TQ0ST) * fma(i_q, par(DPS_S_XQT_XQST), x[DPS_X_EDT] - edst);
 
     alg.p_e = p_e; alg.i_d = i_d; alg.i_q = i_q; alg.v_re = v_re; alg.v_im = v_im; alg.e_fd = e_fd; alg.p_m = p_m;
+}
+
+// True when a limiter of this generator is active at state x: the stabiliser output outside +-H_lim, or a PT1Limited
+// state at / beyond one of its limits (the only situations in which the LIM selects of stage_body change a value).
+template <class PR>
+__device__ __forceinline__ bool stage_at_limit(const double* x, const PR& par, int ctrl) {
+    bool at = false;
+    if (ctrl & DPS_CTRL_PSS) {
+        const bool fed = (ctrl & DPS_CTRL_AVR) != 0;
+        const double omega = x[DPS_X_OMEGA];
+        const double w = par(DPS_S_S_INV_TW) * fma(par(DPS_S_S_KW), (fed ? omega : 0.0), -x[DPS_X_PSS_W]);
+        const double in1 = fed ? w : 0.0;
+        const double o1 = fma(par(DPS_S_S_R1), in1, par(DPS_S_S_OMR1) * x[DPS_X_PSS_LL1]);
+        const double in2 = fed ? o1 : 0.0;
+        const double o2 = fma(par(DPS_S_S_R2), in2, par(DPS_S_S_OMR2) * x[DPS_X_PSS_LL2]);
+        const double hl = par(DPS_S_S_HLIM);
+        at = (o2 < -hl) || (o2 > hl);
+    }
+    if (ctrl & DPS_CTRL_AVR) {
+        const double xe = x[DPS_X_AVR_PT1];
+        at = at || (xe <= par(DPS_S_A_EMIN)) || (xe >= par(DPS_S_A_EMAX));
+    }
+    if (ctrl & DPS_CTRL_GOV) {
+        const double xg = x[DPS_X_GOV_PT1];
+        at = at || (xg <= par(DPS_S_G_VMIN)) || (xg >= par(DPS_S_G_VMAX));
+    }
+    return at;
+}
+
+// VOTE (device only): the caller guarantees that all 32 lanes of the warp are in the call.
+template <bool CTRL, bool VOTE = false, class PR>
+__device__ __forceinline__ void stage_derivatives(const double* x, const PR& par, int ctrl, double fn,
+                                                  double sd, double cd, double v_re, double v_im,
+                                                  double* f, Algebraics& alg) {
+#ifdef __CUDA_ARCH__
+    if (CTRL && VOTE) {
+        if (__any_sync(0xffffffffu, stage_at_limit(x, par, ctrl)))
+            stage_body<CTRL, true>(x, par, ctrl, fn, sd, cd, v_re, v_im, f, alg);
+        else
+            stage_body<CTRL, false>(x, par, ctrl, fn, sd, cd, v_re, v_im, f, alg);
+        return;
+    }
+#endif
+    stage_body<CTRL, true>(x, par, ctrl, fn, sd, cd, v_re, v_im, f, alg);
 }
 
 }  // namespace dps
