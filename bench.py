@@ -143,7 +143,7 @@ def cpu_baseline(sample_sims, batch, threads=None):
     return sample_sims * T_STEPS / dt, dt, out['rec']
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out=sys.stdout):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python/numpy/torch and
     is not present on the GPU box, so this arm times its C restatement (oracle, kind 'port') with every host thread."""
     rank = int(os.environ.get('RANK', '0'))
@@ -171,7 +171,8 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': 'sim-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def workload_config(P, n_gpus, note=None):
@@ -196,8 +197,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
+    # the JSON line must be the only thing on stdout: libraries (NCCL prints its version with printf) get stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
-        return run_reference_arm(args)
+        return run_reference_arm(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -348,7 +353,8 @@ def main():
             'gpu_launches': 2 * args.steps,
             'kernel': info, 'finite_fraction': finite, 'checksum': checksum, 'clocks': clocks,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -262,14 +262,68 @@ def _clamp(x, lo, hi):
     return torch.minimum(torch.maximum(x, lo), hi)
 
 
+def _fingerprint(values):
+    """(key, keep-alive list, any requires_grad) of a list of model attributes: tensors are identified by object identity
+    and version counter (in-place writes bump it, rebinding changes the identity), plain numbers by value."""
+    key, keep, grad = [], [], False
+    for v in values:
+        if torch.is_tensor(v):
+            key.append((id(v), v._version))
+            keep.append(v)                       # a live reference: the id cannot be recycled while the entry exists
+            grad = grad or v.requires_grad
+        else:
+            key.append(v)
+    return tuple(key), keep, grad
+
+
+def _network_inputs(sim):
+    """Every attribute the static admittance matrix and the load flow read."""
+    vals = []
+    for ln in sim.lines:
+        vals += [ln.from_bus_id, ln.to_bus_id, ln.r, ln.x, ln.b]
+    for tr in sim.trafos:
+        vals += [tr.from_bus_id, tr.to_bus_id, tr.r, tr.x, tr.b, tr.s_n, tr.s_n_sys]
+    for bus in sim.busses:
+        vals += [bus.lf_type, bus.voltage]
+        for m in bus.models:
+            if isinstance(m, Shunt):
+                vals += ['shunt', m.y_shunt]
+            elif isinstance(m, SynchMachine):
+                vals += ['gen', m.p_soll_mw, m.s_n_sys]
+            elif isinstance(m, Load):
+                vals += ['load', m.p_soll_mw, m.q_soll_mvar, m.s_n_sys]
+    return vals
+
+
+def _dynamic_inputs(sim):
+    """What the dynamic admittance matrix reads on top of :func:`_network_inputs` (the generator Norton admittances)."""
+    vals = []
+    for _, g in generators_of(sim):
+        vals += [g.x_d_st, g.s_n, g.s_n_sys]
+    return vals
+
+
 def initialize(sim, device):
     """Load flow + model initialisation + Z = inv(Y_dyn) + initial bus voltages.
-    Mirrors simulator.py:438-450.  Everything returned is ``[B,1]`` (B in {1,P}) real float64, except Z0/Ydiag/bus_v."""
+    Mirrors simulator.py:438-450.  Everything returned is ``[B,1]`` (B in {1,P}) real float64, except Z0/Ydiag/bus_v.
+
+    The load flow and ``inv(Y_dyn)`` are pure functions of model attributes that an identification loop does not touch
+    between runs (it varies H, D, X_d', ... per trajectory): their results are memoised on the simulation object, keyed
+    by identity + version of every input tensor, and recomputed whenever any input changed or requires grad."""
     P = sim.parallel_sims
     col = _Cols(P, device, getattr(sim, '_uniform_cache', None))
     res = InitResult()
-    y_static = static_admittance(sim, col)
-    V, s_calc, iters = load_flow(sim, col, y_static)
+    cache = sim.__dict__.setdefault('_prologue_cache', {})
+    loads = [m for bus in sim.busses for m in bus.models if isinstance(m, Load)]
+    lf_key, lf_keep, lf_grad = _fingerprint(_network_inputs(sim))
+    hit = cache.get('lf')
+    if hit is not None and not lf_grad and hit['key'] == lf_key:
+        V, s_calc, iters = hit['out']
+        lf_cached = True
+    else:
+        y_static = static_admittance(sim, col)
+        V, s_calc, iters = load_flow(sim, col, y_static)
+        lf_cached = False
     res.lf_iters = iters
     res.s_calc = s_calc
 
@@ -279,13 +333,21 @@ def initialize(sim, device):
     res.ctrl, res.x0, res.slots, res.xst = [], [], [], []
 
     # loads become constant admittances from the load-flow voltage (static_models.py:515-527)
-    for bi, bus in enumerate(sim.busses):
-        v_bb = V[:, bi:bi + 1]
-        for m in bus.models:
-            if isinstance(m, Load):
-                s_load = (col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys
-                z_load = torch.conj(torch.abs(v_bb) ** 2 / s_load)
-                m.y_load = 1 / z_load
+    if lf_cached:
+        for m, y in zip(loads, hit['y_load']):
+            m.y_load = y
+    else:
+        for bi, bus in enumerate(sim.busses):
+            v_bb = V[:, bi:bi + 1]
+            for m in bus.models:
+                if isinstance(m, Load):
+                    s_load = (col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys
+                    z_load = torch.conj(torch.abs(v_bb) ** 2 / s_load)
+                    m.y_load = 1 / z_load
+        cache.pop('lf', None)
+        cache.pop('dyn', None)
+        if not lf_grad:
+            cache['lf'] = {'key': lf_key, 'keep': lf_keep, 'out': (V, s_calc, iters), 'y_load': [m.y_load for m in loads]}
 
     for bi, g in gens:
         v_bb = V[:, bi:bi + 1]
@@ -375,9 +437,17 @@ def initialize(sim, device):
         g.e_q_t, g.e_d_t, g.e_q_st, g.e_d_st = e_q_t, e_d_t, e_q_st, e_d_st
         g.p_m, g.e_fd = p_m, e_fd
 
-    y_dyn = dynamic_admittance(sim, col)
-    res.Ydiag = torch.diagonal(y_dyn, dim1=1, dim2=2)
-    res.Z0 = torch.linalg.inv(y_dyn)
+    dyn_key, dyn_keep, dyn_grad = _fingerprint(_dynamic_inputs(sim))
+    hit = cache.get('dyn')
+    if hit is not None and lf_cached and not dyn_grad and hit['key'] == dyn_key:
+        res.Ydiag, res.Z0 = hit['out']
+    else:
+        y_dyn = dynamic_admittance(sim, col)
+        res.Ydiag = torch.diagonal(y_dyn, dim1=1, dim2=2)
+        res.Z0 = torch.linalg.inv(y_dyn)
+        cache.pop('dyn', None)
+        if 'lf' in cache and not dyn_grad:
+            cache['dyn'] = {'key': dyn_key, 'keep': dyn_keep, 'out': (res.Ydiag, res.Z0)}
     res.bus_v = V
     return res
 

@@ -187,9 +187,12 @@ class PowerSystemSimulation(object):
         """simulator.py:485-495 / static_models.py:189-197: bus voltages back to the last model's set point (or 1.0),
         cached matrices dropped.  The next run() redoes load flow and initialisation from scratch."""
         P = self.parallel_sims
+        if getattr(self, '_flat_start', None) is None:
+            # one shared (never written) tensor, so that the prologue's memoisation sees the same input after every reset
+            self._flat_start = torch.ones((P, 1), dtype=torch.complex128, device=self.device)
         for bus in self.busses:
             v = getattr(bus.models[-1], 'v_soll', None) if bus.models else None
-            bus.voltage = v if v is not None else torch.ones((P, 1), dtype=torch.complex128, device=self.device)
+            bus.voltage = v if v is not None else self._flat_start
         self.static_y_matrix = None
         self.inverse_dynamic_y_matrix = None
 
