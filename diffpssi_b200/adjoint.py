@@ -17,8 +17,8 @@ def wanted_slots(init, slot_names):
     return want
 
 
-def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec):
-    """-> (g_x0 [G,13,P], g_upar [G,N_SLOTS], g_vpar [n_vary,P] or None)."""
+def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec, want_z=False):
+    """-> (g_x0 [G,13,P], g_upar [G,N_SLOTS], g_vpar [n_vary,P] or None, g_zsub like zsub or None)."""
     engine.require_cuda()
     lib = plan.lib
     topo = plan.topo
@@ -31,11 +31,13 @@ def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec):
     ws_bytes = int(lib.dps_workspace_bytes(plan.handle, P))
     ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
     a_want = (ctypes.c_uint8 * len(want))(*want)
+    # dL/dZsub is accumulated per trajectory ([n_cfg, rows, cols, 2, P], zero-initialised by the caller)
+    gz = torch.zeros(tuple(zsub.shape[:4]) + (P,), dtype=torch.float64, device=dev) if want_z else None
     rc = lib.dps_backward(plan.handle, P, engine._ptr(upar.detach().contiguous()),
                           engine._ptr(vpar.detach().contiguous()) if vpar is not None else None,
                           engine._ptr(zsub), engine._ptr(ckpt), engine._ptr(g_rec), None, a_want,
-                          engine._ptr(g_x0), engine._ptr(gslot), ctypes.c_void_p(ws.data_ptr()), ws_bytes,
-                          engine._stream())
+                          engine._ptr(g_x0), engine._ptr(gslot), engine._ptr(gz),
+                          ctypes.c_void_p(ws.data_ptr()), ws_bytes, engine._stream())
     engine._check(lib, rc, 'dps_backward')
     g_upar = torch.zeros_like(upar)
     g_vpar = torch.zeros_like(vpar) if vpar is not None else None
@@ -50,4 +52,6 @@ def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec):
         else:
             g_upar[i // engine.N_SLOTS, i % engine.N_SLOTS] = gslot[row].sum()     # shared constant: sum over the batch
         row += 1
-    return g_x0, g_upar, g_vpar
+    if gz is not None and zsub.shape[-1] == 1:
+        gz = gz.sum(dim=-1, keepdim=True)          # network shared by the batch: sum over the trajectories
+    return g_x0, g_upar, g_vpar, gz

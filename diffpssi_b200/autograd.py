@@ -3,7 +3,8 @@
 Forward = ``dps_forward`` (one launch for the whole time loop).  Backward = ``dps_backward``, the hand-written
 discrete adjoint over checkpointed steps: what the reference obtains by letting torch autograd record every op of
 simulator.py:523-543 and calling ``loss.sum().backward()`` (optimization_lib/ps_optimization.py:212).
-Gradients are returned with respect to the kernel inputs (x0, uniform constants, per-sim constants); torch then
+Gradients are returned with respect to the kernel inputs (x0, uniform constants, per-sim constants and -- when a network
+parameter requires grad -- the reduced impedance matrices); torch then
 continues through the prologue graph to the user's leaf tensors.
 """
 import torch
@@ -22,6 +23,7 @@ class StepFunction(torch.autograd.Function):
         x_final = torch.empty((G, engine.N_STATES, P), dtype=torch.float64, device=dev)
         n_ck = plan.n_checkpoints()
         ckpt = torch.empty((n_ck, G, engine.N_STATES, P), dtype=torch.float64, device=dev) if n_ck else None
+        zsub = zsub.detach().contiguous()
         plan.forward(P, x0.detach().contiguous(), upar.detach().contiguous(),
                      None if vpar is None else vpar.detach().contiguous(), zsub, rec, x_final, ckpt)
         ctx.plan, ctx.P = plan, P
@@ -37,6 +39,6 @@ class StepFunction(torch.autograd.Function):
         upar, vpar, zsub, ckpt = ctx.saved_tensors
         if not ctx.has_ckpt:
             raise engine.EngineError('backward needs checkpoints: run() saw no tensor requiring grad')
-        g_x0, g_upar, g_vpar = run_backward(ctx.plan, ctx.P, upar, vpar if ctx.has_vpar else None, zsub, ckpt,
-                                            g_rec.contiguous())
-        return None, None, g_x0, g_upar, g_vpar, None
+        g_x0, g_upar, g_vpar, g_zsub = run_backward(ctx.plan, ctx.P, upar, vpar if ctx.has_vpar else None, zsub, ckpt,
+                                                    g_rec.contiguous(), want_z=ctx.needs_input_grad[5])
+        return None, None, g_x0, g_upar, g_vpar, g_zsub

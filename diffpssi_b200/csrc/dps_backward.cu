@@ -15,8 +15,9 @@
 //                          exchanged through shared memory for V = Z I, voltage cotangents for dI = Z^T dV.
 //
 // Thread mapping is the forward kernel's: one thread per (trajectory, generator), a warp = 32 trajectories of one
-// generator, named barrier per 32-trajectory group.  Gradients are produced for x0 and for every constant slot the host
-// marks as wanted; Z is treated as a constant (parameters entering Y_dyn are not differentiable yet).
+// generator, named barrier per 32-trajectory group.  Gradients are produced for x0, for every constant slot the host
+// marks as wanted and -- on request -- for the reduced impedance matrices (dL/dZsub per trajectory; the host chains it
+// through the fault re-reduction and inv(Y_dyn) to x_d'', S_n, load parameters: SURVEY.md section 8f.1).
 #include <cuda_runtime.h>
 #include <string.h>
 #include "dps_internal.h"
@@ -37,6 +38,7 @@ struct BwdParams {
     const double* grad_xf;     // [n_gen][13][P] or null
     double* g_x0;              // [n_gen][13][P]
     double* gslot;             // [n_want][P]
+    double* g_zsub;            // [n_cfg][z_rows][z_cols][2][P] accumulated, or null
     double* scratch;           // [ckpt_stride][n_gen][13][P]
     int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_ckpt, n_seg;
     int seg_step[MAX_SEG];
@@ -59,7 +61,7 @@ __device__ __forceinline__ void bwd_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int G, bool CTRL>
+template <int G, bool CTRL, bool ZGRAD>
 __global__ void __launch_bounds__(BwdCfg<G>::THREADS, 1)
 dps_adjoint_kernel(const BwdParams p) {
     constexpr int GROUPS = BwdCfg<G>::GROUPS;
@@ -260,12 +262,25 @@ dps_adjoint_kernel(const BwdParams p) {
                 // dI = Z^T dV over the generator rows ...
                 const double* xb = exchange(dv_re, dv_im);
                 double di_re = 0.0, di_im = 0.0;
+                // ... and, when the network carries a gradient, dZ[r][g] += dV_r conj(I_g): this thread owns column g of
+                // its trajectory's matrix, so the accumulation in HBM needs no atomics.  I_g is recomputed (6 flops).
+                double own_re = 0.0, own_im = 0.0;
+                double* gz = nullptr;
+                if (ZGRAD) {
+                    injection(X[i], par, sds[i], cds[i], own_re, own_im);
+                    gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
+                }
+                const long long gz_row = (long long)p.z_cols * 2 * P;
                 for (int r = 0; r < p.n_gen; ++r) {
                     double zr, zi;
                     z_at(cfg, r, g, zr, zi);
                     const double ar = xb[r * 64 + lane], ai = xb[r * 64 + 32 + lane];
                     di_re += zr * ar + zi * ai;
                     di_im += -zi * ar + zr * ai;
+                    if (ZGRAD && live) {
+                        gz[r * gz_row] += ar * own_re + ai * own_im;
+                        gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                    }
                 }
                 // ... plus the recorded voltages of extra observed buses (last stage of the step)
                 if (i == n_stages - 1 && p.n_obs > p.n_gen && sim < P) {
@@ -277,6 +292,10 @@ dps_adjoint_kernel(const BwdParams p) {
                         z_at(cfg, r, g, zr, zi);
                         di_re += zr * ar + zi * ai;
                         di_im += -zi * ar + zr * ai;
+                        if (ZGRAD && live) {
+                            gz[r * gz_row] += ar * own_re + ai * own_im;
+                            gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                        }
                     }
                 }
                 injection_vjp(X[i], par, sds[i], cds[i], di_re, di_im, dx, gp, dsd, dcd);
@@ -300,19 +319,20 @@ dps_adjoint_kernel(const BwdParams p) {
     }
 }
 
-template <int G, bool CTRL>
+template <int G, bool CTRL, bool ZGRAD>
 static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
     const size_t smem = sizeof(double) * (G * DPS_N_SLOTS + 2 * C::GROUPS * G * 64) + sizeof(short) * G * DPS_N_SLOTS;
     const long long spb = 32LL * C::GROUPS;
     const long long blocks = (p.P + spb - 1) / spb;
-    dps_adjoint_kernel<G, CTRL><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    dps_adjoint_kernel<G, CTRL, ZGRAD><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int G>
 static cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, cudaStream_t stream) {
-    return ctrl ? launch_bwd_one<G, true>(p, stream) : launch_bwd_one<G, false>(p, stream);
+    if (p.g_zsub != nullptr) return ctrl ? launch_bwd_one<G, true, true>(p, stream) : launch_bwd_one<G, false, true>(p, stream);
+    return ctrl ? launch_bwd_one<G, true, false>(p, stream) : launch_bwd_one<G, false, false>(p, stream);
 }
 
 static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl, cudaStream_t stream) {
@@ -343,7 +363,7 @@ size_t dps_workspace_bytes(const dps_plan* plan, int64_t P) {
 
 int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const double* vpar, const double* zsub,
                  const double* ckpt, const double* grad_rec, const double* grad_x_final, const uint8_t* want,
-                 double* g_x0, double* gslot, void* workspace, size_t workspace_bytes, void* stream) {
+                 double* g_x0, double* gslot, double* g_zsub, void* workspace, size_t workspace_bytes, void* stream) {
     if (!plan) { set_error("dps_backward: null plan"); return 1; }
     if (P < 1) { set_error("dps_backward: P must be >= 1"); return 1; }
     if (plan->topo.ckpt_stride <= 0) { set_error("dps_backward: the plan was created without checkpoints (ckpt_stride = 0)"); return 1; }
@@ -359,7 +379,7 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     const FwdParams& b = plan->base;
     p.P = P; p.n_gen = b.n_gen; p.solver = b.solver; p.n_steps = b.n_steps; p.dt = b.dt; p.fn = b.fn;
     p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.ckpt = ckpt; p.grad_rec = grad_rec; p.grad_xf = grad_x_final;
-    p.g_x0 = g_x0; p.gslot = gslot; p.scratch = (double*)workspace;
+    p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = g_zsub; p.scratch = (double*)workspace;
     p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.z_per_sim = b.z_per_sim;
     p.ckpt_stride = b.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
     p.n_seg = (int)plan->seg_step.size();

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DPS_B200_LIB') or os.path.join(_HERE, 'libdps_b200.so')   # override: kernel A/B experiments
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_STATES = 13
 N_SLOTS = 42
 N_FIELDS = 20
@@ -81,7 +81,7 @@ def load_library(path=None):
                                        i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dbl, vp, vp]
     lib.dps_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dps_forward_range.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.dps_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint8), vp, vp, vp,
+    lib.dps_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint8), vp, vp, vp, vp,
                                  ctypes.c_size_t, vp]
     lib.dps_math_probe.argtypes = [i64, vp, vp, vp, vp]
     lib.dps_fp64_peak_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]

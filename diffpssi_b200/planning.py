@@ -140,6 +140,30 @@ def split_complex_batch_last(z):
     return z.real.permute(perm).contiguous(), z.imag.permute(perm).contiguous()
 
 
+def network_reduce_torch(Z0, Ydiag, obs_bus, gen_bus, cfg_sets, m_max, y_fault=FAULT_ADMITTANCE):
+    """Differentiable torch twin of ``dps_network_reduce`` (csrc/dps_reduce.cuh), used instead of the kernel when a
+    gradient has to flow into the network (``x_d_st``, ``s_n``, loads ... enter ``Y_dyn``).
+
+    ``Z0`` complex [B,n,n], ``Ydiag`` complex [B,n] -> zsub float64 [n_cfg, n_obs+m_max, n_gen+m_max, 2, B] with the
+    rows/columns beyond [n_obs, n_gen] (the kernel's scratch) left at zero.  Each faulted bus is the rank-1 update
+    ``Z' = Z - f Z[:,b] Z[b,:]``, ``f = c/(1 + c Z_bb)``, ``c = y_fault - Y_bb`` of simulator.py:526-528."""
+    B = max(Z0.shape[0], Ydiag.shape[0])
+    rows, cols = len(obs_bus) + m_max, len(gen_bus) + m_max
+    oi = torch.tensor(obs_bus, dtype=torch.long, device=Z0.device)
+    gi = torch.tensor(gen_bus, dtype=torch.long, device=Z0.device)
+    out = []
+    for faulted in cfg_sets:
+        Z = Z0
+        for fb in faulted:
+            c = y_fault - Ydiag[:, fb]
+            f = c / (1 + c * Z[:, fb, fb])
+            Z = Z - f[:, None, None] * Z[:, :, fb:fb + 1] * Z[:, fb:fb + 1, :]
+        sub = Z[:, oi][:, :, gi].expand(B, len(obs_bus), len(gen_bus))            # [B, n_obs, n_gen]
+        sub = torch.nn.functional.pad(torch.view_as_real(sub.resolve_conj()), (0, 0, 0, m_max, 0, m_max))
+        out.append(sub.permute(1, 2, 3, 0))                                        # [rows, cols, 2, B]
+    return torch.stack(out, dim=0).contiguous()
+
+
 def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
     """-> (topo dict for engine.Plan, dict of host-side extras)."""
     step_cfg, cfg_sets = event_schedule(sim.time, sim.sc_events)

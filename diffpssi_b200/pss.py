@@ -232,9 +232,10 @@ class PowerSystemSimulation(object):
         init = self.initialize()
         P, dev = self.parallel_sims, self.device
         rplan = self._trace_recorder(init)
-        needs_grad = torch.is_grad_enabled() and (
+        net_grad = torch.is_grad_enabled() and (init.Z0.requires_grad or init.Ydiag.requires_grad)
+        needs_grad = net_grad or (torch.is_grad_enabled() and (
             any(t.requires_grad for x in init.x0 for t in x) or
-            any(v.requires_grad for sl in init.slots for v in sl.values()))
+            any(v.requires_grad for sl in init.slots for v in sl.values())))
         topo, extras = planning.build_topology(self, init, rplan.channel_keys, self.solver,
                                                self.ckpt_stride if needs_grad else 0)
         x0 = planning.canonical_x0(init, P)
@@ -243,6 +244,7 @@ class PowerSystemSimulation(object):
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
         topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary)
+        topo['want_z'] = bool(net_grad)
         plan = engine.Plan(topo)
         self.last_plan = plan
         with torch.no_grad():
@@ -315,9 +317,15 @@ class PreparedRun(object):
 
     def execute(self):
         engine.require_cuda()
-        with torch.no_grad():
-            self.reduce_network()
-        rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, self.zsub)
+        if self.topo.get('want_z'):
+            # a gradient flows into the network: the fault re-reduction becomes part of the torch graph
+            zsub = planning.network_reduce_torch(self.init.Z0, self.init.Ydiag, self.extras['obs_bus'],
+                                                 self.extras['gen_bus'], self.extras['cfg_sets'], self.extras['m_max'])
+        else:
+            with torch.no_grad():
+                self.reduce_network()
+            zsub = self.zsub
+        rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, zsub)
         return self._assemble(rec), x_final
 
     def _assemble(self, rec):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DPS_ABI_VERSION 1
+#define DPS_ABI_VERSION 2
 
 /* ---- per-generator state layout (canonical: absent controllers keep zero slots) ----------------------------
  * reference order: machine(6) | exciter(lead-lag, PT1) | governor(PT1, lead-lag) | PSS(washout, LL1, LL2)
@@ -188,12 +188,15 @@ int dps_forward_range(const dps_plan* plan, int64_t P, int32_t step_begin, int32
  *   g_x0          out [n_gen][DPS_N_STATES][P]
  *   gslot         out [n_want][P]  per-trajectory gradient of every wanted slot, in the order they appear in `want`
  *                 (the host sums over p when the slot really is shared by the batch); may be NULL if nothing is wanted
+ *   g_zsub        in/out [n_cfg][z_rows][z_cols][2][P] or NULL: per-trajectory dL/dZsub (rows < n_obs, columns < n_gen),
+ *                 ACCUMULATED into a buffer the caller zeroed -- also per trajectory when Zsub is shared by the batch
+ *                 (the host then sums over p).  From V = Z I: dZ[r][j] += dV_r conj(I_j) in (re, im) components.
  *   workspace     device scratch of dps_workspace_bytes(plan, P) bytes
  */
 int dps_backward(const dps_plan* plan, int64_t P,
                  const double* upar, const double* vpar, const double* zsub, const double* ckpt,
                  const double* grad_rec, const double* grad_x_final,
-                 const uint8_t* want, double* g_x0, double* gslot,
+                 const uint8_t* want, double* g_x0, double* gslot, double* g_zsub,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement helper: runs a dependent-chain-free DFMA loop on every SM and returns the achieved fp64

@@ -269,6 +269,40 @@ def grad_cases(sel):
          ('gen', 'G3', 'exciter.pt1_lim.gain_pt1'): 100.0 * rng.uniform(0.8, 1.25, P),
          ('gen', 'G4', 'governor.lead_lag.t_1'): 1.0 * rng.uniform(0.8, 1.25, P)},
         ['G%d.omega' % g for g in (1, 2, 3, 4)] + ['G1.e_q_st', 'G3.e_d_st'], True)
+    network_grad_cases(sel, one)
+
+
+def network_grad_cases(sel, one):
+    """Leaves that enter the dynamic admittance matrix (x_d'' of a generator: synchronous_machine.py:336): the gradient
+    flows through Z = inv(Y_dyn) and through the fault re-reduction (simulator.py:386, 526-528).
+
+    The unmodified reference cannot differentiate this combination: ``Y = inv(Z); Y[:, b, b] = 1e6`` writes in place
+    into the output of ``inv``, which its backward needs ("modified by an inplace operation").  For these cases only,
+    ``torch.linalg.inv`` is wrapped to return a clone -- an identity for the values and for the mathematics of the
+    gradient -- and the result is cross-checked by central finite differences of the forward pass, whose values the
+    wrapper cannot change."""
+    import torch
+    rng = np.random.RandomState(7)
+    orig_inv = torch.linalg.inv
+    torch.linalg.inv = lambda a, **kw: orig_inv(a, **kw).clone()
+    try:
+        _network_grad_cases(sel, one, rng)
+    finally:
+        torch.linalg.inv = orig_inv
+
+
+def _network_grad_cases(sel, one, rng):
+    P = 4
+    one('grad_ibb_z_heun', 'ibb', P, 'heun', 2.0, [(1, 1.05, 'Bus 1')],
+        {('gen', 'Gen 1', 'x_d_st'): 0.23 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.8, 1.5, P)},
+        ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], True)
+    P = 3
+    one('grad_k2a_z_heun', 'k2a', P, 'heun', 1.0, [(0.1, 0.13, 'B1')],
+        {('gen', 'G1', 'x_d_st'): 0.25 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'G3', 'x_d_st'): 0.25 * rng.uniform(0.8, 1.25, P),
+         ('gen', 'G2', 'h'): 6.5 * rng.uniform(0.8, 1.25, P)},
+        ['G%d.omega' % g for g in (1, 2, 3, 4)] + ['G1.e_q_st', 'G3.e_d_st'], True)
 
 
 def main():

@@ -178,8 +178,9 @@ class EmulStepFunction(torch.autograd.Function):
     """CPU stand-in for diffpssi_b200.autograd.StepFunction used by the `not gpu` gradient tests."""
 
     @staticmethod
-    def forward(ctx, prep, x0, upar, vpar, zsub_np):
+    def forward(ctx, prep, x0, upar, vpar, zsub):
         lib = build_emul()
+        zsub_np = np.ascontiguousarray(zsub.detach().numpy()) if torch.is_tensor(zsub) else zsub
         topo = prep.topo
         P = prep.sim.parallel_sims
         T, G = topo['n_steps'], topo['n_gen']
@@ -212,7 +213,10 @@ class EmulStepFunction(torch.autograd.Function):
         g = np.ascontiguousarray(g_rec.numpy())
         g_x0 = np.zeros((G, engine.N_STATES, P))
         gslot = np.zeros((G, engine.N_SLOTS, P))
-        lib.emul_backward(*head, _p(x0n), _p(upn), _p(vpn), _p(zsub_np), _p(g), _p(g_x0), _p(gslot))
+        want_z = ctx.needs_input_grad[4]
+        P_ = g_x0.shape[-1]
+        gz = np.zeros(zsub_np.shape[:4] + (P_,)) if want_z else None
+        lib.emul_backward(*head, _p(x0n), _p(upn), _p(vpn), _p(zsub_np), _p(g), _p(g_x0), _p(gslot), _p(gz))
         g_upar = torch.zeros(upn.shape, dtype=torch.float64)
         g_vpar = torch.zeros(vpn.shape, dtype=torch.float64) if vpn is not None else None
         for i, vi in enumerate(topo['slot_vary']):
@@ -221,7 +225,10 @@ class EmulStepFunction(torch.autograd.Function):
                 g_vpar[vi] = torch.from_numpy(gslot[gi, k])
             else:
                 g_upar[gi, k] = float(gslot[gi, k].sum())
-        return None, torch.from_numpy(g_x0), g_upar, g_vpar, None
+        g_z = None
+        if want_z:
+            g_z = torch.from_numpy(gz if zsub_np.shape[-1] > 1 else gz.sum(axis=-1, keepdims=True))
+        return None, torch.from_numpy(g_x0), g_upar, g_vpar, g_z
 
 
 def run_emulated_autograd(sim):
@@ -242,6 +249,9 @@ def run_emulated_autograd(sim):
                             len(extras['gen_bus']), (ci * len(extras['gen_bus']))(*extras['gen_bus']),
                             len(extras['cfg_sets']), (ci * len(ptr))(*ptr), (ci * max(len(flat), 1))(*flat),
                             ctypes.c_double(planning.FAULT_ADMITTANCE), _p(zsub))
+    if topo.get('want_z'):
+        zsub = planning.network_reduce_torch(prep.init.Z0, prep.init.Ydiag, extras['obs_bus'], extras['gen_bus'],
+                                             extras['cfg_sets'], extras['m_max'])
     rec = EmulStepFunction.apply(prep, prep.x0, prep.upar, prep.vpar, zsub)
     rows = extras['key_rows']
     if rows != list(range(rec.shape[0])):

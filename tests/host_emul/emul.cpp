@@ -149,7 +149,8 @@ extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, doub
                              int z_rows, int z_cols, int n_cfg, const uint8_t* step_cfg, int z_per_sim,
                              const int* slot_vary, int n_rec, const int* rec_chan, long long P, const double* x0,
                              const double* upar, const double* vpar, const double* zsub, const double* grad_rec,
-                             double* g_x0, double* gslot_all /* [n_gen][DPS_N_SLOTS][P] */) {
+                             double* g_x0, double* gslot_all /* [n_gen][DPS_N_SLOTS][P] */,
+                             double* g_zsub /* [n_cfg][z_rows][z_cols][2][P] accumulated, or null */) {
     const int G = n_gen, NS = DPS_N_STATES;
     const int n_stages = solver == DPS_EULER ? 1 : (solver == DPS_HEUN ? 2 : 4);
     const long long zb = z_per_sim ? P : 1;
@@ -250,11 +251,18 @@ extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, doub
                 for (int j = 0; j < G; ++j) {
                     auto par = par_of(j);
                     double di_re = 0, di_im = 0;
+                    double own_re = 0, own_im = 0;
+                    if (g_zsub) injection(&X[i][j * NS], par, SD[i][j], CD[i][j], own_re, own_im);
+                    auto gz_at = [&](int r, int c) { return g_zsub + ((((long long)cfg * z_rows + r) * z_cols + j) * 2 + c) * P + s; };
                     for (int r = 0; r < G; ++r) {
                         double zr, zi;
                         z_at(cfg, r, j, zr, zi);
                         di_re += zr * dvr[r] + zi * dvi[r];
                         di_im += -zi * dvr[r] + zr * dvi[r];
+                        if (g_zsub) {
+                            *gz_at(r, 0) += dvr[r] * own_re + dvi[r] * own_im;
+                            *gz_at(r, 1) += -dvr[r] * own_im + dvi[r] * own_re;
+                        }
                     }
                     if (i == n_stages - 1) {
                         for (int c = 0; c < n_rec; ++c) {
@@ -266,6 +274,11 @@ extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, doub
                             z_at(cfg, r, j, zr, zi);
                             if (kind == DPS_CH_BUS_VRE) { di_re += zr * a; di_im += -zi * a; }
                             else { di_re += zi * a; di_im += zr * a; }
+                            if (g_zsub) {
+                                const double ar = (kind == DPS_CH_BUS_VRE) ? a : 0.0, ai = (kind == DPS_CH_BUS_VRE) ? 0.0 : a;
+                                *gz_at(r, 0) += ar * own_re + ai * own_im;
+                                *gz_at(r, 1) += -ar * own_im + ai * own_re;
+                            }
                         }
                     }
                     injection_vjp(&X[i][j * NS], par, SD[i][j], CD[i][j], di_re, di_im, &dx[j * NS], &gp[j * DPS_N_SLOTS], dsd[j], dcd[j]);

@@ -59,3 +59,32 @@ def test_gradients_tiled_batch_and_shared_parameter():
     h = 1e-6
     fd = (total_loss(0.07 + h) - total_loss(0.07 - h)) / (2 * h)
     assert abs(fd - float(shared.grad.real)) / abs(fd) < 1e-5
+
+
+def test_shared_network_parameter_gradient():
+    """A *uniform* x_d'' leaf ([1,1]) keeps the network shared by the batch: dL/dZsub is summed over the trajectories
+    and chained through the fault re-reduction and inv(Y_dyn).  Checked by central finite differences through the
+    public API (the reference itself cannot differentiate this case: its in-place fault switching breaks autograd)."""
+    tile = 9
+    def build(v, grad):
+        sim, gold, _ = helpers.sim_from_gold('grad_ibb_heun', 'ibb', device='cuda', tile=tile)
+        leaf = torch.tensor([[v + 0j]], dtype=torch.complex128, device='cuda', requires_grad=grad)
+        sim.get_generator_by_name('Gen 1').x_d_st = leaf
+        return sim, gold, leaf
+    def loss_of_run(sim, gold):
+        names = [str(s) for s in gold['names']]
+        idx = [names.index(str(c)) for c in gold['loss_channels']]
+        _, r = sim.run()
+        o = r[:, :, idx]
+        target = torch.from_numpy(gold['target']).to(o.device)[None, :, None] * torch.ones_like(o)
+        return ((o - target) ** 2).mean(dim=(1, 2)).sum()
+    sim, gold, leaf = build(0.23, True)
+    loss = loss_of_run(sim, gold)
+    assert sim.last_plan.topo['z_per_sim'] == 0 and sim.last_plan.topo['want_z']
+    loss.backward()
+    g = float(leaf.grad.real)
+    h = 1e-6
+    lp = float(loss_of_run(*build(0.23 + h, False)[:2]))
+    lm = float(loss_of_run(*build(0.23 - h, False)[:2]))
+    fd = (lp - lm) / (2 * h)
+    assert abs(fd) > 0 and abs(fd - g) / abs(fd) < 1e-5, (fd, g)

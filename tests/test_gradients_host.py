@@ -8,7 +8,9 @@ import torch
 
 from tests import helpers
 
-CASES = [('grad_ibb_heun', 'ibb'), ('grad_ibb_euler', 'ibb'), ('grad_ibb_rk4', 'ibb'), ('grad_k2a_heun', 'k2a')]
+CASES = [('grad_ibb_heun', 'ibb'), ('grad_ibb_euler', 'ibb'), ('grad_ibb_rk4', 'ibb'), ('grad_k2a_heun', 'k2a'),
+         # leaves that enter Y_dyn (x_d''): the gradient also flows through dL/dZsub, the fault re-reduction and inv(Y_dyn)
+         ('grad_ibb_z_heun', 'ibb'), ('grad_k2a_z_heun', 'k2a')]
 
 
 def loss_of(result, gold, names):
