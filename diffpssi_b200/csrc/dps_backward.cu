@@ -206,7 +206,7 @@ dps_adjoint_kernel(const BwdParams p) {
                             for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; x[k] = xs[k] + f[k] * dt; }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + ((acc[k] + f[k]) * dt) / 6.0;
+                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + dps_div6((acc[k] + f[k]) * dt);
                         }
                     }
                 }

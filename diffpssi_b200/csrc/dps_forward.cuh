@@ -295,7 +295,7 @@ dps_step_kernel(const FwdParams p) {
             for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; xt[k] = x[k] + f[k] * dt; }
             eval(xt, f, true);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) x[k] = x[k] + ((acc[k] + f[k]) * dt) / 6.0;
+            for (int k = 0; k < NS; ++k) x[k] = x[k] + dps_div6((acc[k] + f[k]) * dt);
         }
 
         // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim], written with streaming (evict-first)

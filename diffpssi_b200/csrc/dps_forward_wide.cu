@@ -13,8 +13,18 @@
 //   * constants: the register set (machine + set points) may differ per trajectory, controller constants are uniform
 //     (PMODE 1) or common to all generators (PMODE 3).
 // Bound: shared-memory bandwidth of the Z stream (one LDS.128 per complex MAC, no register blocking yet); see DESIGN.md.
+//
+// MMA variant (MMA = true, used whenever its shared-memory footprint fits): the network product of a whole block is ONE
+// real matrix product on the FP64 MMA instruction (mma.sync.m8n8k4.f64):
+//     [V_re | V_im] (G x 2S)  =  Z_re (G x G) [I_re | I_im]  +  Z_im (G x G) [-I_im | I_re]         S = trajectories per block
+// so the 8 columns of an MMA tile are the real and imaginary parts of FOUR trajectories and every tile is full.  Z_re and
+// Z_im sit in shared memory pre-swizzled into A-fragment order (one conflict-free LDS.64 per lane and MMA), the currents
+// are written by their owner threads as rows [column n][generator k] (B-fragment reads are conflict-free because the
+// row stride is 4 mod 8 doubles), warps own (8-generator x 4-trajectory) output tiles and write V back through shared
+// memory.  Per (thread, stage) this replaces 2 G LDS.128 + 4 G DFMA by G/2 MMAs + G LDS.64 per WARP.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "dps_internal.h"
 #include "dps_model.cuh"
 
@@ -22,7 +32,26 @@ namespace dps {
 
 constexpr int WIDE_THREADS = 512;
 
-template <int CM, int PMODE, int SOLVER>
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// shared-memory geometry of the MMA variant
+struct WideMmaGeom {
+    int MT, KT, NT, KP, VS;          // 8-row tiles of Z, 4-column tiles of Z, 8-column tiles of I, padded row of s_B, row of s_V
+    __host__ __device__ WideMmaGeom(int G, int SPB) {
+        MT = (G + 7) / 8; KT = (G + 3) / 4; NT = (SPB + 3) / 4;
+        KP = KT * 4 + (((KT * 4) % 8 == 0) ? 4 : 0);         // == 4 (mod 8): conflict-free B-fragment loads
+        VS = NT * 8 + 1;
+    }
+    __host__ __device__ size_t bytes(int G) const {
+        return sizeof(double) * ((size_t)2 * MT * KT * 32 + (size_t)2 * NT * 8 * KP + (size_t)MT * 8 * VS +
+                                 (size_t)G * (DPS_N_SLOTS + 1));
+    }
+};
+
+template <int CM, int PMODE, int SOLVER, bool MMA>
 __global__ void __launch_bounds__(WIDE_THREADS, 1)
 dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     constexpr bool CTRL = (CM != 0);
@@ -31,9 +60,17 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     const int G = p.n_gen;
     const int GP = WG * 32;                                                       // padded generator count
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // DFMA variant
     double2* s_z = reinterpret_cast<double2*>(smem_raw);                          // [G][G] active configuration, transposed
     double2* s_cur = s_z + G * G;                                                 // [2][SPB][GP]
     double* s_upar = reinterpret_cast<double*>(s_cur + 2 * SPB * GP);             // [G][UPS]
+    // MMA variant
+    const WideMmaGeom mg(G, SPB);
+    double* s_ar = reinterpret_cast<double*>(smem_raw);                           // [MT][KT][32] A fragments of Z_re
+    double* s_ai = s_ar + mg.MT * mg.KT * 32;                                     // ... of Z_im
+    double* s_b = s_ai + mg.MT * mg.KT * 32;                                      // [2][NT*8][KP] currents, row n = column of B
+    double* s_v = s_b + 2 * mg.NT * 8 * mg.KP;                                    // [MT*8][VS] voltages
+    if (MMA) s_upar = s_v + mg.MT * 8 * mg.VS;
 
     const int t = threadIdx.x;
     const int sl = t / GP;                          // trajectory slot in the block
@@ -50,11 +87,26 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
         s_upar[gi * UPS + k] = p.upar[i];
     }
     auto load_z = [&](int cfg) {
-        // transposed copy of configuration cfg: s_z[j*G + g] = Z[g][j]
-        for (int i = t; i < G * G; i += blockDim.x) {
-            const int row = i % G, col = i / G;
-            const double* e = p.zsub + (((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2;
-            s_z[i] = make_double2(e[0], e[1]);
+        if (MMA) {
+            // A-fragment order: lane l of tile (mt, kt) holds Z[mt*8 + l/4][kt*4 + l%4]
+            for (int i = t; i < mg.MT * mg.KT * 32; i += blockDim.x) {
+                const int l = i & 31, tile = i >> 5;
+                const int kt = tile % mg.KT, mt = tile / mg.KT;
+                const int row = mt * 8 + (l >> 2), col = kt * 4 + (l & 3);
+                const bool ok = row < G && col < G;
+                const double* e = p.zsub + (((long long)cfg * p.z_rows + (ok ? row : 0)) * p.z_cols + (ok ? col : 0)) * 2;
+                s_ar[i] = ok ? e[0] : 0.0;
+                s_ai[i] = ok ? e[1] : 0.0;
+            }
+            // padding columns of the current rows stay zero for the whole run
+            for (int i = t; i < 2 * mg.NT * 8 * mg.KP; i += blockDim.x) s_b[i] = 0.0;
+        } else {
+            // transposed copy of configuration cfg: s_z[j*G + g] = Z[g][j]
+            for (int i = t; i < G * G; i += blockDim.x) {
+                const int row = i % G, col = i / G;
+                const double* e = p.zsub + (((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2;
+                s_z[i] = make_double2(e[0], e[1]);
+            }
         }
     };
     int seg = 0;
@@ -97,6 +149,45 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
         if (PMODE == 3) injection(X, par_const, sd, cd, i_re, i_im);
         else injection(X, par_fast, sd, cd, i_re, i_im);
         double2* cb = s_cur + (buf * SPB + ((sl < SPB) ? sl : SPB - 1)) * GP;
+        double v_re, v_im;
+        // MMA variant: rows of this trajectory in the current / voltage tiles (real part, imaginary part 4 rows below)
+        const int slc = (sl < SPB) ? sl : SPB - 1;
+        const int nrow = (slc >> 2) * 8 + (slc & 3);
+        double* bcur = s_b + buf * (mg.NT * 8 * mg.KP);
+        if (MMA) {
+            if (gen_live) {
+                bcur[nrow * mg.KP + gl] = i_re;
+                bcur[(nrow + 4) * mg.KP + gl] = i_im;
+            }
+            __syncthreads();
+            const int lane = t & 31, warp = t >> 5;
+            const int fr = lane >> 2, fk = lane & 3;                     // fragment row (A) / column (B), and k index
+            for (int u = warp; u < mg.MT * mg.NT; u += WIDE_THREADS / 32) {
+                const int mt = u % mg.MT, nt = u / mg.MT;
+                const double* ar = s_ar + (mt * mg.KT) * 32 + lane;
+                const double* ai = s_ai + (mt * mg.KT) * 32 + lane;
+                const double* b1 = bcur + (nt * 8 + fr) * mg.KP + fk;              // [ I_re | I_im ]
+                const double* b2 = bcur + (nt * 8 + ((fr + 4) & 7)) * mg.KP + fk;  // [-I_im | I_re ]
+                const int flip = (fr < 4) ? (int)0x80000000 : 0;                   // sign of -I_im, applied on the integer pipe
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll 5
+                for (int kt = 0; kt < mg.KT; ++kt) {
+                    const double a_r = ar[kt * 32], a_i = ai[kt * 32];
+                    const double x1 = b1[kt * 4];
+                    double x2 = b2[kt * 4];
+                    x2 = __hiloint2double(__double2hiint(x2) ^ flip, __double2loint(x2));
+                    dmma_m8n8k4(d0, d1, a_r, x1);
+                    dmma_m8n8k4(e0, e1, a_i, x2);
+                }
+                double* vo = s_v + (mt * 8 + fr) * mg.VS + nt * 8 + 2 * fk;
+                vo[0] = d0 + e0;
+                vo[1] = d1 + e1;
+            }
+            __syncthreads();
+            v_re = s_v[gl * mg.VS + nrow];
+            v_im = s_v[gl * mg.VS + nrow + 4];
+            buf ^= 1;
+        } else {
         if (sl < SPB) cb[gl] = gen_live ? make_double2(i_re, i_im) : make_double2(0.0, 0.0);
         __syncthreads();
         buf ^= 1;
@@ -110,7 +201,9 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             via = fma(z.x, cj.y, via);
             vib = fma(z.y, cj.x, vib);
         }
-        const double v_re = vra + vrb, v_im = via + vib;
+        v_re = vra + vrb;
+        v_im = via + vib;
+        }
         if (PMODE == 3) stage_derivatives<CTRL>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         else stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         if (last_stage && (rec_mask >> DPS_N_STATES)) {
@@ -129,7 +222,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
                 double br = 0.0, bi = 0.0;
                 for (int j = 0; j < G; ++j) {
                     const double zr_ = __ldg(zbase + 2 * j), zi_ = __ldg(zbase + 2 * j + 1);
-                    const double2 cj = cb[j];
+                    const double2 cj = MMA ? make_double2(bcur[nrow * mg.KP + j], bcur[(nrow + 4) * mg.KP + j]) : cb[j];
                     br += zr_ * cj.x - zi_ * cj.y;
                     bi += zr_ * cj.y + zi_ * cj.x;
                 }
@@ -182,7 +275,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; xt[k] = x[k] + f[k] * dt; }
             eval(xt, f, true);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) x[k] = x[k] + ((acc[k] + f[k]) * dt) / 6.0;
+            for (int k = 0; k < NS; ++k) x[k] = x[k] + dps_div6((acc[k] + f[k]) * dt);
         }
         if (rec_mask & 0x1FFFu) {
             const short* ch = p.rec_chan[g];
@@ -203,9 +296,23 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     }
 }
 
+template <int CM, int PMODE, int SOLVER, bool MMA>
+static cudaError_t launch_wide_kern(const WideParams& p, cudaStream_t stream, int* regs, int* threads_out, int* spb_out);
+
 template <int CM, int PMODE, int SOLVER>
 static cudaError_t launch_wide_one(const WideParams& p, cudaStream_t stream, int* regs, int* threads_out, int* spb_out) {
-    auto kern = dps_step_wide_kernel<CM, PMODE, SOLVER>;
+    // the MMA variant whenever its shared-memory footprint fits (G <= ~104 with all controller tables)
+    const int G = p.n_gen;
+    const int WG = (G + 31) / 32;
+    const int SPB = WIDE_THREADS / (WG * 32);
+    const bool mma = WideMmaGeom(G, SPB).bytes(G) <= 227 * 1024 && getenv("DPS_WIDE_NO_MMA") == nullptr;
+    return mma ? launch_wide_kern<CM, PMODE, SOLVER, true>(p, stream, regs, threads_out, spb_out)
+               : launch_wide_kern<CM, PMODE, SOLVER, false>(p, stream, regs, threads_out, spb_out);
+}
+
+template <int CM, int PMODE, int SOLVER, bool MMA>
+static cudaError_t launch_wide_kern(const WideParams& p, cudaStream_t stream, int* regs, int* threads_out, int* spb_out) {
+    auto kern = dps_step_wide_kernel<CM, PMODE, SOLVER, MMA>;
     const int G = p.n_gen;
     const int WG = (G + 31) / 32;
     const int SPB = WIDE_THREADS / (WG * 32);
@@ -218,7 +325,8 @@ static cudaError_t launch_wide_one(const WideParams& p, cudaStream_t stream, int
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = sizeof(double2) * ((size_t)G * G + 2 * SPB * WG * 32) + sizeof(double) * G * (DPS_N_SLOTS + 1);
+    const size_t smem = MMA ? WideMmaGeom(G, SPB).bytes(G)
+                            : sizeof(double2) * ((size_t)G * G + 2 * SPB * WG * 32) + sizeof(double) * G * (DPS_N_SLOTS + 1);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

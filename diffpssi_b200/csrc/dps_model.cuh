@@ -56,6 +56,13 @@ __device__ __forceinline__ double dps_sqrt(double s) {
     // s is a sum of squares: an integer test of its high word (normal and positive) replaces the FP64 compare
     return (__double2hiint(s) >= 0x00100000) ? res : 0.0;
 }
+// a / 6 (RK4 combination, solvers.py:214): product with the rounded reciprocal plus one residual correction -- correctly
+// rounded except for a vanishing fraction of inputs (then off by one ulp); the IEEE division sequence is ~25 instructions.
+__device__ __forceinline__ double dps_div6(double a) {
+    const double r = 1.0 / 6.0;
+    const double q = a * r;
+    return fma(fma(-q, 6.0, a), r, q);
+}
 // sqrt of a strictly positive normal number: no zero guard (the caller adds a 1e-300 floor for free inside an FMA)
 __device__ __forceinline__ double dps_sqrt_pos(double s) {
     // coupled (Goldschmidt) iteration: g -> sqrt(s), h -> 1/(2 sqrt(s)); five dependent FP64 levels after the MUFU
@@ -96,6 +103,7 @@ inline double dps_rcp(double x) { return 1.0 / x; }
 inline double dps_div(double a, double b) { return a / b; }
 inline double dps_sqrt(double s) { return sqrt(s); }
 inline double dps_sqrt_pos(double s) { return sqrt(s); }
+inline double dps_div6(double a) { return a / 6.0; }
 inline void dps_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 #endif
 
