@@ -31,6 +31,10 @@
 #include "dps_internal.h"
 #include "dps_model.cuh"
 
+#ifndef DPS_REC_SYNC_STEPS
+#define DPS_REC_SYNC_STEPS 16
+#endif
+
 namespace dps {
 
 template <int G>
@@ -49,7 +53,10 @@ struct FwdCfg {
     static constexpr int UPS = DPS_N_SLOTS + 1;    // row stride of the constant table: odd -> conflict-free per-lane rows
 };
 
-template <int G, int CM, int PMODE, int ZPS, int SOLVER>
+// RMASK: compile-time copy of the regular recorder's field mask (dps_internal.h), or -1 for "decide at run time".
+// The recorder of every benchmark configuration -- omega of each generator, mask 0x1 -- then is ONE predicated
+// streaming store per step instead of ~45 instructions of mask tests and channel arithmetic.
+template <int G, int CM, int PMODE, int ZPS, int SOLVER, int RMASK = -1>
 __global__ void __launch_bounds__(FwdCfg<G>::THREADS, FwdCfg<G>::MIN_BLOCKS)
 dps_step_kernel(const FwdParams p) {
     using C = FwdCfg<G>;
@@ -157,8 +164,8 @@ dps_step_kernel(const FwdParams p) {
     const double dt = p.dt, hdt = 0.5 * p.dt;
     const unsigned rec_mask = live ? p.rec_mask[g] : 0u;
     // regular recorder layout (dps_internal.h): launch-uniform field mask, channel = rec_fbase[field] + generator
-    const bool rec_regular = p.rec_regular != 0;
-    const unsigned rec_umask = p.rec_umask;
+    const bool rec_regular = (RMASK >= 0) ? true : (p.rec_regular != 0);
+    const unsigned rec_umask = (RMASK >= 0) ? (unsigned)RMASK : p.rec_umask;
     const long long rec_cs = (long long)p.n_steps * P;                 // channel stride
     double* const rec_thread = p.rec + (long long)g * rec_cs + sim;    // channel g, step 0, this trajectory
     const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
@@ -213,7 +220,7 @@ dps_step_kernel(const FwdParams p) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k)
                     if (rec_umask & (1u << (DPS_N_STATES + k))) {
-                        if (live) __stcs(out + (long long)p.rec_fbase[DPS_N_STATES + k] * rec_cs, av[k]);
+                        if (live) dps_rec_store(out + (long long)p.rec_fbase[DPS_N_STATES + k] * rec_cs, av[k]);
                     }
             }
         } else if (last_stage && (rec_mask >> DPS_N_STATES)) {
@@ -223,7 +230,7 @@ dps_step_kernel(const FwdParams p) {
             const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
 #pragma unroll
             for (int k = 0; k < 7; ++k)
-                if (rec_mask & (1u << (DPS_N_STATES + k))) __stcs(out + ch[DPS_N_STATES + k] * cs, av[k]);
+                if (rec_mask & (1u << (DPS_N_STATES + k))) dps_rec_store(out + ch[DPS_N_STATES + k] * cs, av[k]);
         }
         // extra observed buses (recorded voltages of non-generator buses): last stage only.  Every lane runs the same
         // number of iterations because the shuffles need the whole warp.
@@ -243,14 +250,20 @@ dps_step_kernel(const FwdParams p) {
                 }
                 if (valid) {
                     const int e = rr - p.n_gen;
-                    if (p.obs_chan[e][0] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim, br);
-                    if (p.obs_chan[e][1] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim, bi);
+                    if (p.obs_chan[e][0] >= 0) dps_rec_store(p.rec + ((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim, br);
+                    if (p.obs_chan[e][1] >= 0) dps_rec_store(p.rec + ((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim, bi);
                 }
             }
         }
     };
 
     for (; step < p.step_end; ++step) {
+#if DPS_REC_SYNC_STEPS > 0
+        // The warps of a block are independent; without a bound on their drift the 24-byte pieces they write into the
+        // same 32-byte DRAM sectors of a recorder row arrive further apart than L2 keeps a dirty line, and every piece
+        // costs a read-modify-write.  A block barrier every few steps keeps them within L2's reach.
+        if ((step & (DPS_REC_SYNC_STEPS - 1)) == 0) __syncthreads();
+#endif
         if (step == next_change) {
             ++seg;
             cfg = p.seg_cfg[seg];
@@ -310,13 +323,13 @@ dps_step_kernel(const FwdParams p) {
 #pragma unroll
                         for (int k = grp4; k < grp4 + 4 && k < NS; ++k)
                             if (rec_umask & (1u << k)) {
-                                if (live) __stcs(out + (long long)p.rec_fbase[k] * rec_cs, x[k]);
+                                if (live) dps_rec_store(out + (long long)p.rec_fbase[k] * rec_cs, x[k]);
                             }
                     }
                 }
                 if (NS < DPS_N_STATES) {
                     for (int k = NS; k < DPS_N_STATES; ++k)
-                        if ((rec_umask & (1u << k)) && live) __stcs(out + (long long)p.rec_fbase[k] * rec_cs, 0.0);
+                        if ((rec_umask & (1u << k)) && live) dps_rec_store(out + (long long)p.rec_fbase[k] * rec_cs, 0.0);
                 }
             }
         } else if (rec_mask & 0x1FFFu) {
@@ -328,7 +341,7 @@ dps_step_kernel(const FwdParams p) {
                 if (rec_mask & (0xFu << grp4) & 0x1FFFu) {
 #pragma unroll
                     for (int k = grp4; k < grp4 + 4 && k < DPS_N_STATES; ++k)
-                        if (rec_mask & (1u << k)) __stcs(out + ch[k] * cs, (k < NS) ? x[k < NS ? k : 0] : 0.0);
+                        if (rec_mask & (1u << k)) dps_rec_store(out + ch[k] * cs, (k < NS) ? x[k < NS ? k : 0] : 0.0);
                 }
             }
         }
@@ -346,10 +359,14 @@ dps_step_kernel(const FwdParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // launch helpers (one instantiation set per G, see dps_forward_inst.cu)
 // ---------------------------------------------------------------------------------------------------------
-template <int G, int CM, int PMODE, int ZPS, int SOLVER>
+template <int G, int CM, int PMODE, int ZPS, int SOLVER, int RMASK = -1>
 static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs) {
     using C = FwdCfg<G>;
-    auto kern = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER>;
+    // shared Z + the usual recorder (omega of every generator, regular layout): compile-time recorder mask
+    if constexpr (RMASK < 0 && ZPS == 0 && PMODE != 2 && CM >= 0) {
+        if (p.rec_regular && p.rec_umask == 0x1u) return launch_one<G, CM, PMODE, ZPS, SOLVER, 0x1>(p, stream, regs);
+    }
+    auto kern = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER, RMASK>;
     if (regs) {
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, kern);

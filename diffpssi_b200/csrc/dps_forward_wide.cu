@@ -213,7 +213,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             const double av[7] = {alg.p_e, alg.i_d, alg.i_q, alg.v_re, alg.v_im, alg.e_fd, alg.p_m};
 #pragma unroll
             for (int k = 0; k < 7; ++k)
-                if (rec_mask & (1u << (DPS_N_STATES + k))) __stcs(out + ch[DPS_N_STATES + k] * cs, av[k]);
+                if (rec_mask & (1u << (DPS_N_STATES + k))) dps_rec_store(out + ch[DPS_N_STATES + k] * cs, av[k]);
         }
         // recorded voltages of non-generator buses: row r of the reduced matrix is read from global memory
         if (last_stage && n_extra > 0 && live) {
@@ -227,8 +227,8 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
                     bi += zr_ * cj.y + zi_ * cj.x;
                 }
                 const int e = r - G;
-                if (p.obs_chan[e][0] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim, br);
-                if (p.obs_chan[e][1] >= 0) __stcs(p.rec + ((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim, bi);
+                if (p.obs_chan[e][0] >= 0) dps_rec_store(p.rec + ((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim, br);
+                if (p.obs_chan[e][1] >= 0) dps_rec_store(p.rec + ((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim, bi);
             }
         }
     };
@@ -283,7 +283,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             const long long cs = (long long)p.n_steps * P;
 #pragma unroll
             for (int k = 0; k < DPS_N_STATES; ++k)
-                if (rec_mask & (1u << k)) __stcs(out + ch[k] * cs, (k < NS) ? x[k < NS ? k : 0] : 0.0);
+                if (rec_mask & (1u << k)) dps_rec_store(out + ch[k] * cs, (k < NS) ? x[k < NS ? k : 0] : 0.0);
         }
     }
 

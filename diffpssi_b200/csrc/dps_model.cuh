@@ -107,6 +107,20 @@ inline double dps_div6(double a) { return a / 6.0; }
 inline void dps_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 #endif
 
+// Recorder store.  A warp of the G <= 16 stepper holds 32/G trajectories, so it writes 8*(32/G)-byte pieces of each
+// recorder row and the neighbouring warps complete the 32-byte DRAM sectors a few steps earlier or later.  A plain
+// (write-back) store lets L2 merge the pieces; the streaming hint st.global.cs evicted them half-filled and cost a DRAM
+// read-modify-write per piece (14.1 GB of traffic per launch instead of the algorithmic 10.5 GB, profiles/README.md).
+#ifdef __CUDACC__
+__device__ __forceinline__ void dps_rec_store(double* p, double v) {
+#ifdef DPS_REC_STREAMING
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+#endif
+
 // Reads constant `slot` of the generator this thread works on.  UP = uniform table in shared memory,
 // VARY=true adds the per-sim override path.
 template <bool VARY>
