@@ -31,6 +31,9 @@
 #include "dps_internal.h"
 #include "dps_model.cuh"
 
+#ifndef DPS_Z_PAIRS
+#define DPS_Z_PAIRS 0
+#endif
 #ifndef DPS_REC_SYNC_STEPS
 #define DPS_REC_SYNC_STEPS 16
 #endif
@@ -64,13 +67,17 @@ dps_step_kernel(const FwdParams p) {
     constexpr bool CTRL = (CM != 0);                 // CM: -1 = per-generator controller flags, else the common flag set
     constexpr int NS = CTRL ? DPS_N_STATES : 6;      // live states per generator
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // ZPS==0: Z of every configuration, transposed: [n_cfg][col j][row g], real and imaginary parts in separate planes.
-    // The G lanes of a trajectory read G consecutive doubles (LDS.64: the three trajectory groups of a warp hit the same
-    // addresses, two conflict-free wavefronts per load).  The interleaved (re, im) LDS.128 version of r1m needed 7
-    // wavefronts per load (4 ideal + bank conflicts between the groups) and kept the shared-memory pipe 69 % busy.
+    // ZPS==0: Z of every configuration in shared memory, real and imaginary parts in separate planes.
+    //  default: transposed [n_cfg][col j][row g], one LDS.64 per element: the G lanes of a trajectory read G consecutive
+    //    doubles and the trajectory groups of a warp hit the same addresses (2 conflict-free wavefronts per load).
+    //  DPS_Z_PAIRS (experiment, off): row-major [n_cfg][row g][RS], RS = G rounded up to even; a lane reads TWO consecutive
+    //    elements of its row per LDS.128.  10 loads of Z per stage instead of 20 and 3.6 % fewer instructions, but the
+    //    quarter-warps that straddle two trajectory groups conflict and the loads arrive later: 37.0 ms vs 35.3 ms.
+    //  (The interleaved (re, im) LDS.128 layout of r1m needed 7 wavefronts per load.)
+    constexpr int RS = DPS_Z_PAIRS ? ((G + 1) & ~1) : G;
     double* s_zr = reinterpret_cast<double*>(smem_raw);
-    double* s_zi = s_zr + (ZPS == 0 ? p.n_cfg * G * G : 0);
-    double2* s_cur = reinterpret_cast<double2*>(s_zi + (ZPS == 0 ? p.n_cfg * G * G : 0));   // [WARPS][2][32] exchange lines
+    double* s_zi = s_zr + (ZPS == 0 ? p.n_cfg * G * RS : 0);
+    double2* s_cur = reinterpret_cast<double2*>(s_zi + (ZPS == 0 ? p.n_cfg * G * RS : 0));   // [WARPS][2][32] exchange lines
     double* s_upar = reinterpret_cast<double*>(s_cur + C::WARPS * 64);           // [G][UPS]
     short* s_vary = reinterpret_cast<short*>(s_upar + G * UPS);                  // [G][DPS_N_SLOTS]
 
@@ -96,10 +103,10 @@ dps_step_kernel(const FwdParams p) {
     // (template G > n_gen) contribute exactly 0 to V = Z I without a per-stage select
     for (int i = threadIdx.x; i < C::WARPS * 64; i += blockDim.x) s_cur[i] = make_double2(0.0, 0.0);
     if (ZPS == 0) {
-        for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
-            const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
+        for (int i = threadIdx.x; i < p.n_cfg * G * RS; i += blockDim.x) {
+            const int row = DPS_Z_PAIRS ? (i / RS) % G : i % G, col = DPS_Z_PAIRS ? i % RS : (i / G) % G, cfg = i / (G * RS);
             const bool ok = row < p.n_gen && col < p.n_gen;
-            const double* e = p.zsub + (((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2;
+            const double* e = p.zsub + (((long long)cfg * p.z_rows + (ok ? row : 0)) * p.z_cols + (ok ? col : 0)) * 2;
             s_zr[i] = ok ? e[0] : 0.0;
             s_zi[i] = ok ? e[1] : 0.0;
         }
@@ -149,8 +156,8 @@ dps_step_kernel(const FwdParams p) {
                 zi[ZPS ? j : 0] = ok ? __ldg(zbase + (long long)(2 * j + 1) * zb) : 0.0;
             }
         } else {
-            zcol_r = s_zr + cfg * G * G + gl;
-            zcol_i = s_zi + cfg * G * G + gl;
+            zcol_r = s_zr + cfg * G * RS + (DPS_Z_PAIRS ? gl * RS : gl);
+            zcol_i = s_zi + cfg * G * RS + (DPS_Z_PAIRS ? gl * RS : gl);
         }
     };
 
@@ -168,6 +175,14 @@ dps_step_kernel(const FwdParams p) {
     const unsigned rec_umask = (RMASK >= 0) ? (unsigned)RMASK : p.rec_umask;
     const long long rec_cs = (long long)p.n_steps * P;                 // channel stride
     double* const rec_thread = p.rec + (long long)g * rec_cs + sim;    // channel g, step 0, this trajectory
+    constexpr int N_RUN = (RMASK >= 0) ? __builtin_popcount((unsigned)RMASK & 0x1FFFu) : 0;
+    double* rec_run[N_RUN > 0 ? N_RUN : 1];                            // RMASK: &rec[channel of field][step][sim]
+    if (RMASK >= 0) {
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < DPS_N_STATES; ++k)
+            if ((RMASK >> k) & 1) rec_run[q++] = rec_thread + (long long)p.rec_fbase[k] * rec_cs + (long long)p.step_begin * P;
+    }
     const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
     int step = p.step_begin;
     int buf = 0;
@@ -195,17 +210,37 @@ dps_step_kernel(const FwdParams p) {
         // V_g = sum_j Z[g][j] I_j   (solvers.py:83; zero injections at non-generator buses are skipped).
         // Two partial sums per component keep four independent DFMA chains in flight.
         double vra = 0.0, vrb = 0.0, via = 0.0, vib = 0.0;
+        if (ZPS == 0 && DPS_Z_PAIRS) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const double2 cj = cgrp[j];
-            const double jr = cj.x, ji = cj.y;
-            double zre, zim;
-            if (ZPS) { zre = zr[ZPS ? j : 0]; zim = zi[ZPS ? j : 0]; }
-            else { zre = zcol_r[j * G]; zim = zcol_i[j * G]; }
-            vra = fma(zre, jr, vra);
-            vrb = fma(-zim, ji, vrb);
-            via = fma(zre, ji, via);
-            vib = fma(zim, jr, vib);
+            for (int jp = 0; jp < RS / 2; ++jp) {
+                const double2 zr2 = reinterpret_cast<const double2*>(zcol_r)[jp];
+                const double2 zi2 = reinterpret_cast<const double2*>(zcol_i)[jp];
+                const double2 ca = cgrp[2 * jp];
+                vra = fma(zr2.x, ca.x, vra);
+                vrb = fma(-zi2.x, ca.y, vrb);
+                via = fma(zr2.x, ca.y, via);
+                vib = fma(zi2.x, ca.x, vib);
+                if (2 * jp + 1 < G) {
+                    const double2 cb = cgrp[2 * jp + 1];
+                    vra = fma(zr2.y, cb.x, vra);
+                    vrb = fma(-zi2.y, cb.y, vrb);
+                    via = fma(zr2.y, cb.y, via);
+                    vib = fma(zi2.y, cb.x, vib);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const double2 cj = cgrp[j];
+                const double jr = cj.x, ji = cj.y;
+                double zre, zim;
+                if (ZPS) { zre = zr[ZPS ? j : 0]; zim = zi[ZPS ? j : 0]; }
+                else { zre = zcol_r[j * G]; zim = zcol_i[j * G]; }
+                vra = fma(zre, jr, vra);
+                vrb = fma(-zim, ji, vrb);
+                via = fma(zre, ji, via);
+                vib = fma(zim, jr, vib);
+            }
         }
         const double v_re = vra + vrb, v_im = via + vib;
         if (PMODE == 3) stage_derivatives<CTRL, true>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
@@ -311,10 +346,18 @@ dps_step_kernel(const FwdParams p) {
             for (int k = 0; k < NS; ++k) x[k] = x[k] + dps_div6((acc[k] + f[k]) * dt);
         }
 
-        // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim], written with streaming (evict-first)
-        // stores so the 10 GB output stream does not push the kernel's small working set out of L2.  Fields are tested in groups of
-        // four so an all-clear group costs one branch.  (Algebraics were stored by the last stage evaluation.)
-        if (rec_regular) {
+        // recorder: post-step states (simulator.py:540-543); rec[chan][step][sim].  (Algebraics were stored by the last
+        // stage evaluation.)  Compile-time mask: one running pointer per recorded field, advanced by P per step.
+        if (RMASK >= 0) {
+            int q = 0;
+#pragma unroll
+            for (int k = 0; k < DPS_N_STATES; ++k)
+                if ((RMASK >> k) & 1) {
+                    if (live) dps_rec_store(rec_run[q], (k < NS) ? x[k < NS ? k : 0] : 0.0);
+                    rec_run[q] += P;
+                    ++q;
+                }
+        } else if (rec_regular) {
             if (rec_umask & 0x1FFFu) {
                 double* out = rec_thread + (long long)step * P;
 #pragma unroll
@@ -374,7 +417,8 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = sizeof(double) * (G * C::UPS + (ZPS == 0 ? p.n_cfg * G * G * 2 : 0)) +
+    constexpr int RS = DPS_Z_PAIRS ? ((G + 1) & ~1) : G;
+    const size_t smem = sizeof(double) * (G * C::UPS + (ZPS == 0 ? p.n_cfg * G * RS * 2 : 0)) +
                         sizeof(short) * G * DPS_N_SLOTS + sizeof(double2) * C::WARPS * 64;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

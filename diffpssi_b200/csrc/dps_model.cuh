@@ -202,13 +202,16 @@ struct Pt1Lim {
     }
     __device__ __forceinline__ double gate(double dx) const {
 #ifdef __CUDA_ARCH__
+        // one predicate, one masking of the two words (the short-circuit form compiled into a cascade of six selects)
         const int hw = __double2hiint(dx), lw = __double2loint(dx);
         const bool neg = hw < 0;
-        const bool pos = !neg && ((hw | lw) != 0);
+        const bool pos = (hw >= 0) & ((hw | lw) != 0);
+        const int keep = ((le & neg) | (ge & pos)) ? 0 : -1;
+        return __hiloint2double(hw & keep, lw & keep);
 #else
         const bool neg = dx < 0.0, pos = dx > 0.0;
-#endif
         return ((le && neg) || (ge && pos)) ? 0.0 : dx;
+#endif
     }
 };
 

@@ -19,8 +19,8 @@ PY
 done
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
 for v in $TRAFFIC; do      # light capture: DRAM bytes of one stepping-kernel launch
-  DPS_B200_LIB=$PWD/gpurun_variants/libdps_$v.so ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:dps_step_kernel -s 1 -c 1 --csv --log-file gpurun_out/traffic_${TAG}_$v.csv $CMD > /dev/null 2>&1
-  echo "$v: $(grep -o '"dram__bytes[^,]*","[^"]*","[^"]*"' gpurun_out/traffic_${TAG}_$v.csv | tr '\n' ' ')"
+  DPS_B200_LIB=$PWD/gpurun_variants/libdps_$v.so ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active --clock-control none -k regex:dps_step_kernel -s 1 -c 1 --csv --log-file gpurun_out/traffic_${TAG}_$v.csv $CMD > /dev/null 2>&1
+  echo "$v: $(grep -o '"\(dram__bytes\|smsp__inst\|sm__inst\)[^,]*","[^"]*","[^"]*"' gpurun_out/traffic_${TAG}_$v.csv | tr '\n' ' ')"
 done
 for v in $PROFILE; do
   DPS_B200_LIB=$PWD/gpurun_variants/libdps_$v.so ncu --set full --clock-control none --import-source on -k regex:dps_step_kernel -s 1 -c 1 -o gpurun_out/prof_${TAG}_$v $CMD > gpurun_out/ncu_full_$v.log 2>&1
