@@ -57,29 +57,37 @@ def canonical_x0(init, P):
     return torch.stack(rows, dim=0).contiguous()
 
 
-def pack_slots(init, P, device):
-    """upar [G,42] (uniform constants), vpar [n_vary,P] (per-sim constants), slot_vary list[G*42]."""
-    G = len(init.slots)
+def pack_slots(init, P, device, memo=None):
+    """upar [G,42] (uniform constants), vpar [n_vary,P] (per-sim constants), slot_vary list[G*42].
+
+    ``memo`` (a dict living on the simulation): upar is rebuilt only when one of the uniform slot tensors is a different
+    object than in the previous run (the prologue memoises them, so in an identification loop they are not)."""
     zero1 = torch.zeros(1, dtype=F64, device=device)
-    urows, vrows, slot_vary = [], [], []
+    uniform, vrows, slot_vary, key = [], [], [], []
     for sl in init.slots:
-        ucols = []
         for name in SLOTS:
             v = sl.get(name)
-            if v is None:
-                ucols.append(zero1)
-                slot_vary.append(-1)
-                continue
-            v = v.reshape(-1).to(F64)
-            if v.shape[0] == 1:
-                ucols.append(v)
-                slot_vary.append(-1)
+            if v is None or v.shape[0] != 1 and v.numel() != 1:
+                uniform.append(None)
+                key.append(None)
+                if v is None:
+                    slot_vary.append(-1)
+                else:
+                    slot_vary.append(len(vrows))
+                    vrows.append(v.reshape(-1).to(F64))
             else:
-                ucols.append(zero1)
-                slot_vary.append(len(vrows))
-                vrows.append(v)
-        urows.append(torch.cat(ucols))
-    upar = torch.stack(urows, dim=0).contiguous()
+                uniform.append(v)
+                key.append((id(v), v._version))
+                slot_vary.append(-1)
+    G = len(init.slots)
+    hit = memo.get('upar') if memo is not None else None
+    no_grad = not any(v is not None and v.requires_grad for v in uniform)
+    if hit is not None and no_grad and hit[0] == key:
+        upar = hit[2]
+    else:
+        upar = torch.cat([zero1 if v is None else v.reshape(-1).to(F64) for v in uniform]).reshape(G, N_SLOTS).contiguous()
+        if memo is not None and no_grad:
+            memo['upar'] = (key, uniform, upar)
     vpar = torch.stack(vrows, dim=0).contiguous() if vrows else None
     return upar, vpar, slot_vary
 
@@ -166,7 +174,12 @@ def network_reduce_torch(Z0, Ydiag, obs_bus, gen_bus, cfg_sets, m_max, y_fault=F
 
 def build_topology(sim, init, channel_keys, solver_name, ckpt_stride=0):
     """-> (topo dict for engine.Plan, dict of host-side extras)."""
-    step_cfg, cfg_sets = event_schedule(sim.time, sim.sc_events)
+    ev_key = (len(sim.time), float(sim.time_step), tuple((e.start_time, e.end_time, int(e.bus)) for e in sim.sc_events))
+    hit = sim.__dict__.get('_schedule_cache')
+    if hit is None or hit[0] != ev_key:                # the per-step Python loop costs milliseconds: once per event list
+        hit = (ev_key,) + event_schedule(sim.time, sim.sc_events)
+        sim.__dict__['_schedule_cache'] = hit
+    step_cfg, cfg_sets = hit[1], hit[2]
     obs_bus, chans, rows = observed_rows(init, channel_keys)
     G = len(init.gens)
     if G > engine.MAX_GW:

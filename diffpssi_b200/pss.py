@@ -239,7 +239,7 @@ class PowerSystemSimulation(object):
         topo, extras = planning.build_topology(self, init, rplan.channel_keys, self.solver,
                                                self.ckpt_stride if needs_grad else 0)
         x0 = planning.canonical_x0(init, P)
-        upar, vpar, slot_vary = planning.pack_slots(init, P, dev)
+        upar, vpar, slot_vary = planning.pack_slots(init, P, dev, self.__dict__.setdefault('_pack_cache', {}))
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
