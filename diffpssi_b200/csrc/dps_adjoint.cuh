@@ -40,10 +40,10 @@ struct AlgCot {                 // cotangents of the recorded algebraics (non-ze
 // Transpose of stage_derivatives().  Inputs: the stage's forward inputs (x, sd, cd, v), the cotangent df[13] of the
 // derivatives and the cotangent `ac` of the algebraics.  Accumulates into dx[13], gp[DPS_N_SLOTS] and returns the
 // cotangents of (sin d, cos d) and of the bus voltage.
-template <bool CTRL, class PR>
+template <bool CTRL, class PR, class GP>
 __device__ __forceinline__ void stage_vjp(const double* x, const PR& par, int ctrl, double fn, double sd, double cd,
                                           double v_re, double v_im, const double* df, const AlgCot& ac,
-                                          double* dx, double* gp, double& dsd, double& dcd, double& dv_re, double& dv_im) {
+                                          double* dx, GP& gp, double& dsd, double& dcd, double& dv_re, double& dv_im) {
     const double omega = x[DPS_X_OMEGA];
     const double eqst = x[DPS_X_EQST], edst = x[DPS_X_EDST], eqt = x[DPS_X_EQT], edt = x[DPS_X_EDT];
     // ---- forward recompute of the algebraic chain --------------------------------------------------------------------
@@ -284,9 +284,9 @@ __device__ __forceinline__ void stage_vjp(const double* x, const PR& par, int ct
 }
 
 // Transpose of injection(): given the cotangent (di_re, di_im) of this generator's Norton current.
-template <class PR>
+template <class PR, class GP>
 __device__ __forceinline__ void injection_vjp(const double* x, const PR& par, double sd, double cd, double di_re,
-                                              double di_im, double* dx, double* gp, double& dsd, double& dcd) {
+                                              double di_im, double* dx, GP& gp, double& dsd, double& dcd) {
     const double ixd = par(DPS_S_INV_XDST), ixq = par(DPS_S_INV_XQST), snr = par(DPS_S_SNR);
     const double a = x[DPS_X_EQST] * ixd, b = x[DPS_X_EDST] * ixq;
     gp[DPS_S_SNR] += di_re * (a * sd - b * cd) + di_im * (-(a * cd) - b * sd);

@@ -1,0 +1,330 @@
+// dps_backward.cuh -- the discrete-adjoint kernel (sm_100a), instantiated per generator count by dps_backward_inst.cu
+// (one translation unit per G so the build parallelises); ABI entry points and dispatch: dps_backward.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+#include "dps_internal.h"
+#include "dps_adjoint.cuh"
+#include "dps_backward_params.h"
+
+namespace dps {
+
+template <int G>
+struct BwdCfg {
+    static constexpr int GROUPS = (G >= 3) ? 1 : (G == 2 ? 2 : 4);
+    static constexpr int THREADS = 32 * G * GROUPS;
+};
+
+__device__ __forceinline__ void bwd_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Gradient accumulators of the constant slots.  N = how many leading slots are kept (0: no slot gradient is wanted, the
+// whole parameter-gradient arithmetic of stage_vjp is dead code; DPS_N_REG_SLOTS: only machine constants / set points --
+// the usual identification leaves H, D, X_d', ...; DPS_N_SLOTS: everything).  Indices are literals at every use, so
+// writes beyond N fold into a dead dummy.
+template <int N>
+struct SlotGrads {
+    double v[N > 0 ? N : 1];
+    double dummy;
+    __device__ __forceinline__ double& operator[](int k) { return (k < N) ? v[k < N ? k : 0] : dummy; }
+};
+
+template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP>
+__global__ void __launch_bounds__(BwdCfg<G>::THREADS, 1)
+dps_adjoint_kernel(const BwdParams p) {
+    constexpr int GROUPS = BwdCfg<G>::GROUPS;
+    constexpr int NS = DPS_N_STATES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_upar = reinterpret_cast<double*>(smem_raw);                        // [G][DPS_N_SLOTS]
+    double* s_xch = s_upar + G * DPS_N_SLOTS;                                    // [2][GROUPS][G][2][32]
+    short* s_vary = reinterpret_cast<short*>(s_xch + 2 * GROUPS * G * 64);       // [G][DPS_N_SLOTS]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gw = warp % G;
+    const int grp = warp / G;
+    const bool gen_live = gw < p.n_gen;
+    const int g = gen_live ? gw : p.n_gen - 1;
+    const long long P = p.P;
+    const long long sim = ((long long)blockIdx.x * GROUPS + grp) * 32 + lane;
+    const bool live = (sim < P) && gen_live;
+    const long long s = (sim < P) ? sim : (P - 1);
+
+    for (int i = threadIdx.x; i < G * DPS_N_SLOTS; i += blockDim.x) {
+        const bool ok = (i / DPS_N_SLOTS) < p.n_gen;
+        s_upar[i] = ok ? p.upar[i] : 0.0;
+        s_vary[i] = ok ? p.slot_vary[i] : (short)-1;
+    }
+    __syncthreads();
+
+    ParamReader<true> par;
+    par.up = s_upar + g * DPS_N_SLOTS;
+    par.sv = s_vary + g * DPS_N_SLOTS;
+    par.vpar = p.vpar;
+    par.P = P;
+    par.s = s;
+    const int ctrl = CTRL ? p.ctrl[g] : 0;
+    const long long zb = p.z_per_sim ? P : 1;
+    const long long zs = p.z_per_sim ? s : 0;
+    const int bar_id = grp + 1;
+    double* xch_grp = s_xch + (long long)grp * G * 64;
+    int buf = 0;
+
+    // exchange (a, b) with the other generators of this trajectory; afterwards xb[j*64 + lane] / [j*64+32+lane] hold
+    // generator j's pair
+    auto exchange = [&](double a, double b) -> const double* {
+        double* xb = xch_grp + buf * (GROUPS * G * 64);
+        xb[gw * 64 + lane] = gen_live ? a : 0.0;
+        xb[gw * 64 + 32 + lane] = gen_live ? b : 0.0;
+        bwd_barrier(bar_id, 32 * G);
+        buf ^= 1;
+        return xb;
+    };
+    auto z_at = [&](int cfg, int row, int col, double& zr, double& zi) {
+        const double* e = p.zsub + ((((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2) * zb + zs;
+        zr = __ldg(e);
+        zi = __ldg(e + zb);
+    };
+    // one stage evaluation at X: sin/cos, network voltage, derivatives
+    auto eval_stage = [&](const double* X, int cfg, double& sd, double& cd, double& v_re, double& v_im, double* f,
+                          Algebraics& alg) {
+        dps_sincos(X[DPS_X_DELTA], &sd, &cd);
+        double i_re, i_im;
+        injection(X, par, sd, cd, i_re, i_im);
+        const double* xb = exchange(i_re, i_im);
+        v_re = 0.0;
+        v_im = 0.0;
+        for (int j = 0; j < p.n_gen; ++j) {
+            double zr, zi;
+            z_at(cfg, g, j, zr, zi);
+            const double jr = xb[j * 64 + lane], ji = xb[j * 64 + 32 + lane];
+            v_re += zr * jr - zi * ji;
+            v_im += zr * ji + zi * jr;
+        }
+        stage_derivatives<CTRL>(X, par, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+    };
+    auto cfg_of = [&](int step) {
+        int seg = 0;
+        while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= step) ++seg;
+        return p.seg_cfg[seg];
+    };
+
+    // the scheme is a template parameter: the stage loops unroll and X[i], sds[i], ... are registers, not a local array
+    constexpr int n_stages = (SOLVER == DPS_EULER) ? 1 : (SOLVER == DPS_HEUN ? 2 : 4);
+    const double dt = p.dt;
+    // c_i, b_i of the explicit scheme (Euler b=[1]; Heun c=[0,1], b=[1/2,1/2]; RK4 c=[0,1/2,1/2,1], b=[1/6,1/3,1/3,1/6])
+    constexpr double cst[4] = {0.0, (SOLVER == DPS_HEUN) ? 1.0 : 0.5, 0.5, 1.0};
+    constexpr double bst[4] = {(SOLVER == DPS_EULER) ? 1.0 : (SOLVER == DPS_HEUN ? 0.5 : 1.0 / 6.0),
+                               (SOLVER == DPS_HEUN) ? 0.5 : 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+
+    double lam[NS];
+    SlotGrads<NGP> gp;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        lam[k] = (p.grad_xf != nullptr) ? p.grad_xf[((long long)g * NS + k) * P + s] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NGP; ++k) gp.v[k] = 0.0;
+    gp.dummy = 0.0;
+
+    const unsigned rec_mask = p.rec_mask[g];
+    const short* ch = p.rec_chan[g];
+    const long long cs = (long long)p.n_steps * P;
+    const int C = p.ckpt_stride;
+
+    for (int ck = p.n_ckpt - 1; ck >= 0; --ck) {
+        const int k0 = ck * C;
+        const int k1 = (k0 + C < p.n_steps) ? (k0 + C) : p.n_steps;
+        // ---- re-integrate the segment, keeping the state at the start of every step ----------------------------------
+        {
+            double x[NS], xs[NS], acc[NS], f[NS];
+            const double* src = p.ckpt + (((long long)ck * p.n_gen + g) * NS) * P + s;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) x[k] = src[(long long)k * P];
+            for (int step = k0; step < k1; ++step) {
+                if (live) {
+                    double* dst = p.scratch + (((long long)(step - k0) * p.n_gen + g) * NS) * P + s;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) dst[(long long)k * P] = x[k];
+                }
+                if (step == k1 - 1) break;
+                const int cfg = cfg_of(step);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) xs[k] = x[k];
+#pragma unroll
+                for (int st = 0; st < n_stages; ++st) {
+                    double sd, cd, v_re, v_im;
+                    Algebraics alg;
+                    eval_stage(x, cfg, sd, cd, v_re, v_im, f, alg);
+                    if (SOLVER == DPS_EULER) {
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) x[k] = xs[k] + f[k] * dt;
+                    } else if (SOLVER == DPS_HEUN) {
+                        if (st == 0) {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; x[k] = xs[k] + f[k] * dt; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + ((acc[k] + f[k]) * 0.5) * dt;
+                        }
+                    } else {
+                        if (st == 0) {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; x[k] = xs[k] + (f[k] * dt) * 0.5; }
+                        } else if (st == 1) {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; x[k] = xs[k] + (f[k] * dt) * 0.5; }
+                        } else if (st == 2) {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; x[k] = xs[k] + f[k] * dt; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + dps_div6((acc[k] + f[k]) * dt);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- backward sweep over the segment --------------------------------------------------------------------------
+        for (int step = k1 - 1; step >= k0; --step) {
+            const int cfg = cfg_of(step);
+            double X[4][NS], sds[4], cds[4], vres[4], vims[4];
+            {
+                const double* src = p.scratch + (((long long)(step - k0) * p.n_gen + g) * NS) * P + s;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) X[0][k] = src[(long long)k * P];
+            }
+            // recorded post-step states: rec[.., step] = x_{step+1}
+            if (live && rec_mask) {
+                const double* gr = p.grad_rec + (long long)step * P + sim;
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (rec_mask & (1u << k)) lam[k] += gr[ch[k] * cs];
+            }
+            // stage inputs and their voltages
+#pragma unroll
+            for (int i = 0; i < n_stages; ++i) {
+                double f[NS];
+                Algebraics alg;
+                eval_stage(X[i], cfg, sds[i], cds[i], vres[i], vims[i], f, alg);
+                if (i + 1 < n_stages) {
+                    const double ci = cst[i + 1];
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) X[i + 1][k] = X[0][k] + ci * (f[k] * dt);
+                }
+            }
+            // transposed stages, last to first
+            double sum_dx[NS], dxn[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { sum_dx[k] = 0.0; dxn[k] = 0.0; }
+#pragma unroll
+            for (int i = n_stages - 1; i >= 0; --i) {
+                double dk[NS], dx[NS];
+                const double bi = bst[i] * dt;
+                const double cn = (i + 1 < n_stages) ? cst[i + 1] * dt : 0.0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) { dk[k] = bi * lam[k] + cn * dxn[k]; dx[k] = 0.0; }
+                AlgCot ac = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                if (i == n_stages - 1 && live && (rec_mask >> NS)) {
+                    const double* gr = p.grad_rec + (long long)step * P + sim;
+                    double* av[7] = {&ac.p_e, &ac.i_d, &ac.i_q, &ac.v_re, &ac.v_im, &ac.e_fd, &ac.p_m};
+#pragma unroll
+                    for (int k = 0; k < 7; ++k)
+                        if (rec_mask & (1u << (NS + k))) *av[k] = gr[ch[NS + k] * cs];
+                }
+                double dsd, dcd, dv_re, dv_im;
+                stage_vjp<CTRL>(X[i], par, ctrl, p.fn, sds[i], cds[i], vres[i], vims[i], dk, ac, dx, gp, dsd, dcd, dv_re, dv_im);
+                // dI = Z^T dV over the generator rows ...
+                const double* xb = exchange(dv_re, dv_im);
+                double di_re = 0.0, di_im = 0.0;
+                // ... and, when the network carries a gradient, dZ[r][g] += dV_r conj(I_g): this thread owns column g of
+                // its trajectory's matrix, so the accumulation in HBM needs no atomics.  I_g is recomputed (6 flops).
+                double own_re = 0.0, own_im = 0.0;
+                double* gz = nullptr;
+                if (ZGRAD) {
+                    injection(X[i], par, sds[i], cds[i], own_re, own_im);
+                    gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
+                }
+                const long long gz_row = (long long)p.z_cols * 2 * P;
+                for (int r = 0; r < p.n_gen; ++r) {
+                    double zr, zi;
+                    z_at(cfg, r, g, zr, zi);
+                    const double ar = xb[r * 64 + lane], ai = xb[r * 64 + 32 + lane];
+                    di_re += zr * ar + zi * ai;
+                    di_im += -zi * ar + zr * ai;
+                    if (ZGRAD && live) {
+                        gz[r * gz_row] += ar * own_re + ai * own_im;
+                        gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                    }
+                }
+                // ... plus the recorded voltages of extra observed buses (last stage of the step)
+                if (i == n_stages - 1 && p.n_obs > p.n_gen && sim < P) {
+                    for (int r = p.n_gen; r < p.n_obs; ++r) {
+                        const int e = r - p.n_gen;
+                        const double ar = (p.obs_chan[e][0] >= 0) ? p.grad_rec[((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim] : 0.0;
+                        const double ai = (p.obs_chan[e][1] >= 0) ? p.grad_rec[((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim] : 0.0;
+                        double zr, zi;
+                        z_at(cfg, r, g, zr, zi);
+                        di_re += zr * ar + zi * ai;
+                        di_im += -zi * ar + zr * ai;
+                        if (ZGRAD && live) {
+                            gz[r * gz_row] += ar * own_re + ai * own_im;
+                            gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                        }
+                    }
+                }
+                injection_vjp(X[i], par, sds[i], cds[i], di_re, di_im, dx, gp, dsd, dcd);
+                dx[DPS_X_DELTA] += dsd * cds[i] - dcd * sds[i];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) { dxn[k] = dx[k]; sum_dx[k] += dx[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) lam[k] += sum_dx[k];
+        }
+    }
+
+    if (live) {
+        double* dst = p.g_x0 + (long long)g * NS * P + s;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) dst[(long long)k * P] = lam[k];
+        const short* wr = p.want_row + g * DPS_N_SLOTS;
+#pragma unroll
+        for (int k = 0; k < NGP; ++k)
+            if (wr[k] >= 0) p.gslot[(long long)wr[k] * P + s] = gp.v[k];
+    }
+}
+
+template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP>
+static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
+    using C = BwdCfg<G>;
+    const size_t smem = sizeof(double) * (G * DPS_N_SLOTS + 2 * C::GROUPS * G * 64) + sizeof(short) * G * DPS_N_SLOTS;
+    const long long spb = 32LL * C::GROUPS;
+    const long long blocks = (p.P + spb - 1) / spb;
+    dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int G, bool CTRL, bool ZGRAD, int SOLVER>
+static cudaError_t launch_bwd_ngp(const BwdParams& p, int ngp, cudaStream_t stream) {
+    // accumulators for the register slots only (machine constants / set points: the usual identification leaves) or for
+    // every slot; the network-gradient variant is only built with all of them (it is the rare one)
+    if constexpr (!ZGRAD) {
+        if (ngp <= DPS_N_REG_SLOTS) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS>(p, stream);
+    }
+    return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS>(p, stream);
+}
+
+template <int G, bool CTRL, bool ZGRAD>
+static cudaError_t launch_bwd_solver(const BwdParams& p, int ngp, cudaStream_t stream) {
+    if (p.solver == DPS_EULER) return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_EULER>(p, ngp, stream);
+    if (p.solver == DPS_HEUN) return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_HEUN>(p, ngp, stream);
+    return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_RK4>(p, ngp, stream);
+}
+
+template <int G>
+cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, int ngp, cudaStream_t stream) {
+    if (p.g_zsub != nullptr) return ctrl ? launch_bwd_solver<G, true, true>(p, ngp, stream) : launch_bwd_solver<G, false, true>(p, ngp, stream);
+    return ctrl ? launch_bwd_solver<G, true, false>(p, ngp, stream) : launch_bwd_solver<G, false, false>(p, ngp, stream);
+}
+
+}  // namespace dps

@@ -1,0 +1,32 @@
+// dps_backward_params.h -- kernel parameter block of the adjoint (shared by dps_backward.cu and dps_backward.cuh).
+#pragma once
+#include "dps_internal.h"
+
+namespace dps {
+
+struct BwdParams {
+    long long P;
+    int n_gen, solver, n_steps;
+    double dt, fn;
+    const double* upar;
+    const double* vpar;
+    const double* zsub;
+    const double* ckpt;        // [n_ckpt][n_gen][13][P]
+    const double* grad_rec;    // [n_rec][n_steps][P]
+    const double* grad_xf;     // [n_gen][13][P] or null
+    double* g_x0;              // [n_gen][13][P]
+    double* gslot;             // [n_want][P]
+    double* g_zsub;            // [n_cfg][z_rows][z_cols][2][P] accumulated, or null
+    double* scratch;           // [ckpt_stride][n_gen][13][P]
+    int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_ckpt, n_seg;
+    int seg_step[MAX_SEG];
+    int seg_cfg[MAX_SEG];
+    int ctrl[MAX_G];
+    unsigned rec_mask[MAX_G];
+    short rec_chan[MAX_G][DPS_N_FIELDS];
+    short obs_chan[MAX_EXTRA_OBS][2];
+    short slot_vary[MAX_G * DPS_N_SLOTS];
+    short want_row[MAX_G * DPS_N_SLOTS];
+};
+
+}  // namespace dps

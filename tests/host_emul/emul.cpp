@@ -245,8 +245,9 @@ extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, doub
                             if (rec_chan[3 * c] == DPS_CH_GEN && rec_chan[3 * c + 1] == g && rec_chan[3 * c + 2] >= NS)
                                 *av[rec_chan[3 * c + 2] - NS] += grad_rec[((long long)c * n_steps + step) * P + s];
                     }
+                    double* gpg = &gp[g * DPS_N_SLOTS];
                     stage_vjp<true>(&X[i][g * NS], par, ctrl[g], fn, SD[i][g], CD[i][g], VR[i][g], VI[i][g], &dk[g * NS], ac,
-                                    &dx[g * NS], &gp[g * DPS_N_SLOTS], dsd[g], dcd[g], dvr[g], dvi[g]);
+                                    &dx[g * NS], gpg, dsd[g], dcd[g], dvr[g], dvi[g]);
                 }
                 for (int j = 0; j < G; ++j) {
                     auto par = par_of(j);
@@ -281,7 +282,8 @@ extern "C" int emul_backward(int n_gen, int solver, int n_steps, double dt, doub
                             }
                         }
                     }
-                    injection_vjp(&X[i][j * NS], par, SD[i][j], CD[i][j], di_re, di_im, &dx[j * NS], &gp[j * DPS_N_SLOTS], dsd[j], dcd[j]);
+                    double* gpj = &gp[j * DPS_N_SLOTS];
+                    injection_vjp(&X[i][j * NS], par, SD[i][j], CD[i][j], di_re, di_im, &dx[j * NS], gpj, dsd[j], dcd[j]);
                     dx[j * NS + DPS_X_DELTA] += dsd[j] * CD[i][j] - dcd[j] * SD[i][j];
                 }
                 dxn = dx;
