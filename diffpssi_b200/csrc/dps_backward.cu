@@ -79,6 +79,7 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = g_zsub; p.scratch = (double*)workspace;
     p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.z_per_sim = b.z_per_sim;
     p.ckpt_stride = b.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
+    p.fast_par = (plan->pmode != 2) ? 1 : 0;
     p.n_seg = (int)plan->seg_step.size();
     for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[i]; p.seg_cfg[i] = plan->seg_cfg[i]; }
     memcpy(p.ctrl, b.ctrl, sizeof(p.ctrl));

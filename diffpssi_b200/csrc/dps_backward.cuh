@@ -30,7 +30,16 @@ struct SlotGrads {
     __device__ __forceinline__ double& operator[](int k) { return (k < N) ? v[k < N ? k : 0] : dummy; }
 };
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP>
+template <bool FAST>
+struct ReaderPick {
+    __device__ __forceinline__ static const ParamRegs& get(const ParamRegs& a, const ParamReader<true>&) { return a; }
+};
+template <>
+struct ReaderPick<false> {
+    __device__ __forceinline__ static const ParamReader<true>& get(const ParamRegs&, const ParamReader<true>& b) { return b; }
+};
+
+template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
 __global__ void __launch_bounds__(BwdCfg<G>::THREADS, 1)
 dps_adjoint_kernel(const BwdParams p) {
     constexpr int GROUPS = BwdCfg<G>::GROUPS;
@@ -58,12 +67,22 @@ dps_adjoint_kernel(const BwdParams p) {
     }
     __syncthreads();
 
-    ParamReader<true> par;
-    par.up = s_upar + g * DPS_N_SLOTS;
-    par.sv = s_vary + g * DPS_N_SLOTS;
-    par.vpar = p.vpar;
-    par.P = P;
-    par.s = s;
+    // Constants.  FASTPAR (plan pmode 1/3: only the DPS_N_REG_SLOTS leading slots may differ per trajectory): those are
+    // resolved once into registers, the controller constants are warp-uniform shared-memory reads.  Otherwise every read
+    // goes through the per-slot vary table (two loads and a branch per use).
+    ParamReader<true> par_gen;
+    par_gen.up = s_upar + g * DPS_N_SLOTS;
+    par_gen.sv = s_vary + g * DPS_N_SLOTS;
+    par_gen.vpar = p.vpar;
+    par_gen.P = P;
+    par_gen.s = s;
+    double pm[FASTPAR ? DPS_N_REG_SLOTS : 1];
+    if (FASTPAR) {
+#pragma unroll
+        for (int k = 0; k < DPS_N_REG_SLOTS; ++k) pm[FASTPAR ? k : 0] = par_gen(k);
+    }
+    const ParamRegs par_fast{pm, s_upar + g * DPS_N_SLOTS};
+    const auto& par = ReaderPick<FASTPAR>::get(par_fast, par_gen);
     const int ctrl = CTRL ? p.ctrl[g] : 0;
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
@@ -81,11 +100,11 @@ dps_adjoint_kernel(const BwdParams p) {
         buf ^= 1;
         return xb;
     };
-    auto z_at = [&](int cfg, int row, int col, double& zr, double& zi) {
-        const double* e = p.zsub + ((((long long)cfg * p.z_rows + row) * p.z_cols + col) * 2) * zb + zs;
-        zr = __ldg(e);
-        zi = __ldg(e + zb);
-    };
+    // Z[cfg][row][col] = (zsub[..][0][b], zsub[..][1][b]).  Row g (V = Z I) and column g (dI = Z^T dV) of the active
+    // configuration are walked with a running pointer: one 64-bit add per element instead of the full index product.
+    const long long z_col_stride = 2 * zb;                              // (row, col) -> (row, col+1)
+    const long long z_row_stride = (long long)p.z_cols * 2 * zb;        // (row, col) -> (row+1, col)
+    auto z_cfg = [&](int cfg) { return p.zsub + ((long long)cfg * p.z_rows * p.z_cols * 2) * zb + zs; };
     // one stage evaluation at X: sin/cos, network voltage, derivatives
     auto eval_stage = [&](const double* X, int cfg, double& sd, double& cd, double& v_re, double& v_im, double* f,
                           Algebraics& alg) {
@@ -95,9 +114,9 @@ dps_adjoint_kernel(const BwdParams p) {
         const double* xb = exchange(i_re, i_im);
         v_re = 0.0;
         v_im = 0.0;
-        for (int j = 0; j < p.n_gen; ++j) {
-            double zr, zi;
-            z_at(cfg, g, j, zr, zi);
+        const double* zp = z_cfg(cfg) + g * z_row_stride;
+        for (int j = 0; j < p.n_gen; ++j, zp += z_col_stride) {
+            const double zr = __ldg(zp), zi = __ldg(zp + zb);
             const double jr = xb[j * 64 + lane], ji = xb[j * 64 + 32 + lane];
             v_re += zr * jr - zi * ji;
             v_im += zr * ji + zi * jr;
@@ -246,9 +265,9 @@ dps_adjoint_kernel(const BwdParams p) {
                     gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
                 }
                 const long long gz_row = (long long)p.z_cols * 2 * P;
-                for (int r = 0; r < p.n_gen; ++r) {
-                    double zr, zi;
-                    z_at(cfg, r, g, zr, zi);
+                const double* zp = z_cfg(cfg) + g * z_col_stride;
+                for (int r = 0; r < p.n_gen; ++r, zp += z_row_stride) {
+                    const double zr = __ldg(zp), zi = __ldg(zp + zb);
                     const double ar = xb[r * 64 + lane], ai = xb[r * 64 + 32 + lane];
                     di_re += zr * ar + zi * ai;
                     di_im += -zi * ar + zr * ai;
@@ -263,8 +282,8 @@ dps_adjoint_kernel(const BwdParams p) {
                         const int e = r - p.n_gen;
                         const double ar = (p.obs_chan[e][0] >= 0) ? p.grad_rec[((long long)p.obs_chan[e][0] * p.n_steps + step) * P + sim] : 0.0;
                         const double ai = (p.obs_chan[e][1] >= 0) ? p.grad_rec[((long long)p.obs_chan[e][1] * p.n_steps + step) * P + sim] : 0.0;
-                        double zr, zi;
-                        z_at(cfg, r, g, zr, zi);
+                        const double* ze = z_cfg(cfg) + r * z_row_stride + g * z_col_stride;
+                        const double zr = __ldg(ze), zi = __ldg(ze + zb);
                         di_re += zr * ar + zi * ai;
                         di_im += -zi * ar + zr * ai;
                         if (ZGRAD && live) {
@@ -294,13 +313,13 @@ dps_adjoint_kernel(const BwdParams p) {
     }
 }
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP>
+template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
 static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
     const size_t smem = sizeof(double) * (G * DPS_N_SLOTS + 2 * C::GROUPS * G * 64) + sizeof(short) * G * DPS_N_SLOTS;
     const long long spb = 32LL * C::GROUPS;
     const long long blocks = (p.P + spb - 1) / spb;
-    dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -308,10 +327,13 @@ template <int G, bool CTRL, bool ZGRAD, int SOLVER>
 static cudaError_t launch_bwd_ngp(const BwdParams& p, int ngp, cudaStream_t stream) {
     // accumulators for the register slots only (machine constants / set points: the usual identification leaves) or for
     // every slot; the network-gradient variant is only built with all of them (it is the rare one)
+    // fast constants whenever the plan allows it and the common accumulator set is enough; the generic reader with all
+    // accumulators covers everything else
     if constexpr (!ZGRAD) {
-        if (ngp <= DPS_N_REG_SLOTS) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS>(p, stream);
+        if (ngp <= DPS_N_REG_SLOTS && p.fast_par) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS, true>(p, stream);
+        if (p.fast_par) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, true>(p, stream);
     }
-    return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS>(p, stream);
+    return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, false>(p, stream);
 }
 
 template <int G, bool CTRL, bool ZGRAD>

@@ -19,6 +19,7 @@ struct BwdParams {
     double* g_zsub;            // [n_cfg][z_rows][z_cols][2][P] accumulated, or null
     double* scratch;           // [ckpt_stride][n_gen][13][P]
     int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_ckpt, n_seg;
+    int fast_par;              // plan pmode 1/3: only the DPS_N_REG_SLOTS leading slots may differ per trajectory
     int seg_step[MAX_SEG];
     int seg_cfg[MAX_SEG];
     int ctrl[MAX_G];
