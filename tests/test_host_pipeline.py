@@ -133,3 +133,93 @@ def test_tiled_grid_host_pipeline_against_oracle():
     res, info = helpers.run_emulated(sim)
     ref = adapter.run_oracle_for(sim, info['init'], rec_channels=rec, full=False)
     assert np.abs(res - ref['rec'].transpose(2, 1, 0)).max() < 1e-9
+
+
+def _init_fingerprint(init):
+    parts = [init.Z0.detach().reshape(-1), init.Ydiag.detach().reshape(-1), init.bus_v.detach().reshape(-1)]
+    flat = [torch.view_as_real(p.resolve_conj()).reshape(-1) if p.is_complex() else p for p in parts]
+    for x0, sl in zip(init.x0, init.slots):
+        flat += [v.detach().reshape(-1).to(torch.float64) for v in x0]
+        flat += [sl[k].detach().reshape(-1).to(torch.float64) for k in sorted(sl)]
+    return [f.clone() for f in flat]
+
+
+def _same(a, b):
+    return len(a) == len(b) and all(x.shape == y.shape and torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_prologue_memoisation_is_invalidated_by_every_kind_of_change():
+    """initialize() memoises the load flow, inv(Y_dyn) and every derived model constant on identity + version of their
+    input tensors (prologue.py).  A cached run must be bit-identical to an uncached one, and every way of changing a
+    model attribute -- rebinding a generator parameter, writing into a load tensor in place, replacing a controller
+    parameter, changing a line -- must reach the result exactly as in a simulation built from scratch."""
+    P = 5
+    rng = np.random.RandomState(3)
+    h_new = 6.5 * rng.uniform(0.8, 1.2, P)
+
+    def fresh(mods):
+        sim = Pss(parallel_sims=P, sim_time=0.1, time_step=0.005, solver='heun', grid_data=helpers.load_grid('k2a'),
+                  verbose=False, device='cpu')
+        for m in mods:
+            m(sim)
+        sim.reset()
+        return sim
+
+    def rebind_h(sim):
+        sim.get_generator_by_name('G2').h = torch.tensor(h_new.reshape(P, 1), dtype=torch.complex128)
+
+    def load_in_place(sim):
+        load = next(m for b in sim.busses for m in b.models if type(m).__name__ == 'Load')
+        load.p_soll_mw.mul_(1.03)                                   # same object, version counter bumped
+
+    def avr_gain(sim):
+        sim.get_generator_by_name('G3').exciter.pt1_lim.gain_pt1 = torch.full((P, 1), 150.0, dtype=torch.float64)
+
+    def line_x(sim):
+        sim.lines[2].x = sim.lines[2].x * 1.1
+
+    sim = fresh([])
+    base = _init_fingerprint(sim.initialize())
+    sim.reset()
+    assert _same(_init_fingerprint(sim.initialize()), base)          # pure cache hit
+    applied = []
+    for mod in (rebind_h, load_in_place, avr_gain, line_x):
+        applied.append(mod)
+        mod(sim)
+        sim.reset()
+        got = _init_fingerprint(sim.initialize())
+        want = _init_fingerprint(fresh(applied).initialize())
+        assert _same(got, want), mod.__name__
+        assert not _same(got, base)
+        sim.reset()
+        assert _same(_init_fingerprint(sim.initialize()), got)      # and the new state is cached consistently
+
+
+def test_network_reduce_torch_matches_device_code():
+    """The differentiable torch twin of the fault re-reduction (planning.network_reduce_torch, used when a gradient flows
+    into the network) equals the host build of the device code (csrc/dps_reduce.cuh) on a per-sim network with single and
+    double faults."""
+    import ctypes
+    rng = np.random.RandomState(0)
+    B, n = 3, 7
+    y = rng.randn(B, n, n) + 1j * rng.randn(B, n, n)
+    y = y + np.transpose(y, (0, 2, 1)) + (8 + 4j) * np.eye(n)
+    Z0 = torch.linalg.inv(torch.from_numpy(y))
+    Yd = torch.diagonal(torch.from_numpy(y), dim1=1, dim2=2)
+    obs_bus, gen_bus, cfg_sets, m_max = [1, 4, 6, 2], [1, 4, 6], [(), (3,), (0, 5)], 2
+    mine = planning.network_reduce_torch(Z0, Yd, obs_bus, gen_bus, cfg_sets, m_max).numpy()
+    lib = helpers.build_emul()
+    z_re, z_im = (a.numpy() for a in planning.split_complex_batch_last(Z0))
+    yd_re, yd_im = (a.numpy() for a in planning.split_complex_batch_last(Yd))
+    ref = np.zeros((len(cfg_sets), len(obs_bus) + m_max, len(gen_bus) + m_max, 2, B))
+    ci = ctypes.c_int
+    ptr, flat = [0], []
+    for s in cfg_sets:
+        flat += list(s)
+        ptr.append(len(flat))
+    p_ = helpers._p
+    lib.emul_network_reduce(ctypes.c_longlong(B), n, p_(z_re), p_(z_im), p_(yd_re), p_(yd_im), len(obs_bus),
+                            (ci * len(obs_bus))(*obs_bus), len(gen_bus), (ci * len(gen_bus))(*gen_bus), len(cfg_sets),
+                            (ci * len(ptr))(*ptr), (ci * len(flat))(*flat), ctypes.c_double(planning.FAULT_ADMITTANCE), p_(ref))
+    no, ng = len(obs_bus), len(gen_bus)
+    assert np.abs(mine[:, :no, :ng] - ref[:, :no, :ng]).max() < 1e-12
