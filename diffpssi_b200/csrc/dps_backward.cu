@@ -14,10 +14,11 @@
 //                          The network couples the generators of one trajectory in both directions: currents are
 //                          exchanged through shared memory for V = Z I, voltage cotangents for dI = Z^T dV.
 //
-// Thread mapping is the forward kernel's: one thread per (trajectory, generator), a warp = 32 trajectories of one
-// generator, named barrier per 32-trajectory group.  Gradients are produced for x0, for every constant slot the host
-// marks as wanted and -- on request -- for the reduced impedance matrices (dL/dZsub per trajectory; the host chains it
-// through the fault re-reduction and inv(Y_dyn) to x_d'', S_n, load parameters: SURVEY.md section 8f.1).
+// Thread mapping is the forward kernel's (dps_forward.cuh): one thread per (trajectory, generator), the generators of a
+// trajectory in adjacent lanes of one warp, exchanges through the warp's private shared-memory line.  Gradients are
+// produced for x0, for every constant slot the host marks as wanted and -- on request -- for the reduced impedance
+// matrices (dL/dZsub per trajectory; the host chains it through the fault re-reduction and inv(Y_dyn) to x_d'', S_n, load
+// parameters: SURVEY.md section 8f.1).  Kernel: dps_backward.cuh (one translation unit per generator count).
 #include <cuda_runtime.h>
 #include <string.h>
 #include "dps_internal.h"
@@ -77,7 +78,7 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     p.P = P; p.n_gen = b.n_gen; p.solver = b.solver; p.n_steps = b.n_steps; p.dt = b.dt; p.fn = b.fn;
     p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.ckpt = ckpt; p.grad_rec = grad_rec; p.grad_xf = grad_x_final;
     p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = g_zsub; p.scratch = (double*)workspace;
-    p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.z_per_sim = b.z_per_sim;
+    p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.n_cfg = b.n_cfg; p.z_per_sim = b.z_per_sim;
     p.ckpt_stride = b.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
     p.fast_par = (plan->pmode != 2) ? 1 : 0;
     p.n_seg = (int)plan->seg_step.size();

@@ -9,15 +9,18 @@
 
 namespace dps {
 
+// Thread mapping = the forward stepper's (dps_forward.cuh): one thread per (trajectory, generator), the G generators of a
+// trajectory in G adjacent lanes of ONE warp (32/G trajectories per warp).  Currents (for V = Z I) and voltage
+// cotangents (for dI = Z^T dV) are exchanged through the warp's private shared-memory line behind a __syncwarp: no block
+// barrier, warps never wait for each other.  (Until r2p a warp held 32 trajectories of one generator and the G warps of a
+// group met at a named barrier twice per stage: one block of 10 warps per SM in lockstep, 28 % FP64-pipe activity.)
 template <int G>
 struct BwdCfg {
-    static constexpr int GROUPS = (G >= 3) ? 1 : (G == 2 ? 2 : 4);
-    static constexpr int THREADS = 32 * G * GROUPS;
+    static constexpr int SPW = 32 / G;             // trajectories per warp
+    static constexpr int WARPS = 4;
+    static constexpr int THREADS = 32 * WARPS;
 };
 
-__device__ __forceinline__ void bwd_barrier(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // Gradient accumulators of the constant slots.  N = how many leading slots are kept (0: no slot gradient is wanted, the
 // whole parameter-gradient arithmetic of stage_vjp is dead code; DPS_N_REG_SLOTS: only machine constants / set points --
@@ -40,23 +43,33 @@ struct ReaderPick<false> {
 };
 
 template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
-__global__ void __launch_bounds__(BwdCfg<G>::THREADS, 1)
+__global__ void __launch_bounds__(BwdCfg<G>::THREADS, 2)
 dps_adjoint_kernel(const BwdParams p) {
-    constexpr int GROUPS = BwdCfg<G>::GROUPS;
+    using Cfg = BwdCfg<G>;
+    constexpr int SPW = Cfg::SPW;
     constexpr int NS = DPS_N_STATES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_upar = reinterpret_cast<double*>(smem_raw);                        // [G][DPS_N_SLOTS]
-    double* s_xch = s_upar + G * DPS_N_SLOTS;                                    // [2][GROUPS][G][2][32]
-    short* s_vary = reinterpret_cast<short*>(s_xch + 2 * GROUPS * G * 64);       // [G][DPS_N_SLOTS]
+    double2* s_xch = reinterpret_cast<double2*>(smem_raw);                       // [WARPS][2][32] exchange lines
+    double* s_upar = reinterpret_cast<double*>(s_xch + Cfg::WARPS * 64);         // [G][DPS_N_SLOTS]
+    // network shared by the batch: Z of every configuration in shared memory, (re, im) planes, in both orientations --
+    // s_zt[cfg][j][g] = Z[g][j] for V = Z I (lanes of a trajectory read consecutive doubles) and s_zn[cfg][r][g] = Z[r][g]
+    // for dI = Z^T dV -- so the two products are LDS with compile-time offsets instead of pointer-chasing global loads
+    const int n_cfg_s = p.z_per_sim ? 0 : p.n_cfg;
+    double* s_ztr = s_upar + G * DPS_N_SLOTS;
+    double* s_zti = s_ztr + n_cfg_s * G * G;
+    double* s_znr = s_zti + n_cfg_s * G * G;
+    double* s_zni = s_znr + n_cfg_s * G * G;
+    short* s_vary = reinterpret_cast<short*>(s_zni + n_cfg_s * G * G);           // [G][DPS_N_SLOTS]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int gw = warp % G;
-    const int grp = warp / G;
-    const bool gen_live = gw < p.n_gen;
-    const int g = gen_live ? gw : p.n_gen - 1;
+    const int sl = lane / G;                       // trajectory slot inside the warp
+    const int gl = lane - sl * G;                  // generator slot
+    const int base = ((sl < SPW) ? sl : SPW - 1) * G;       // first lane of this trajectory's generator group
+    const bool gen_live = (sl < SPW) && (gl < p.n_gen);
+    const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
-    const long long sim = ((long long)blockIdx.x * GROUPS + grp) * 32 + lane;
+    const long long sim = ((long long)blockIdx.x * Cfg::WARPS + warp) * SPW + sl;
     const bool live = (sim < P) && gen_live;
     const long long s = (sim < P) ? sim : (P - 1);
 
@@ -64,6 +77,18 @@ dps_adjoint_kernel(const BwdParams p) {
         const bool ok = (i / DPS_N_SLOTS) < p.n_gen;
         s_upar[i] = ok ? p.upar[i] : 0.0;
         s_vary[i] = ok ? p.slot_vary[i] : (short)-1;
+    }
+    // exchange lines start at zero; only live generator lanes ever store (padding lanes contribute exact zeros)
+    for (int i = threadIdx.x; i < Cfg::WARPS * 64; i += blockDim.x) s_xch[i] = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < n_cfg_s * G * G; i += blockDim.x) {
+        const int a = i % G, b = (i / G) % G, cfg = i / (G * G);           // s_zt[cfg][b][a] = Z[a][b];  s_zn[cfg][b][a] = Z[b][a]
+        const bool ok = a < p.n_gen && b < p.n_gen;
+        const double* et = p.zsub + (((long long)cfg * p.z_rows + (ok ? a : 0)) * p.z_cols + (ok ? b : 0)) * 2;
+        const double* en = p.zsub + (((long long)cfg * p.z_rows + (ok ? b : 0)) * p.z_cols + (ok ? a : 0)) * 2;
+        s_ztr[i] = ok ? et[0] : 0.0;
+        s_zti[i] = ok ? et[1] : 0.0;
+        s_znr[i] = ok ? en[0] : 0.0;
+        s_zni[i] = ok ? en[1] : 0.0;
     }
     __syncthreads();
 
@@ -86,19 +111,16 @@ dps_adjoint_kernel(const BwdParams p) {
     const int ctrl = CTRL ? p.ctrl[g] : 0;
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
-    const int bar_id = grp + 1;
-    double* xch_grp = s_xch + (long long)grp * G * 64;
+    double2* xch_w = s_xch + warp * 64;
     int buf = 0;
 
-    // exchange (a, b) with the other generators of this trajectory; afterwards xb[j*64 + lane] / [j*64+32+lane] hold
-    // generator j's pair
-    auto exchange = [&](double a, double b) -> const double* {
-        double* xb = xch_grp + buf * (GROUPS * G * 64);
-        xb[gw * 64 + lane] = gen_live ? a : 0.0;
-        xb[gw * 64 + 32 + lane] = gen_live ? b : 0.0;
-        bwd_barrier(bar_id, 32 * G);
+    // exchange (a, b) with the other generators of this trajectory; afterwards xb[j] holds generator j's pair
+    auto exchange = [&](double a, double b) -> const double2* {
+        double2* cw = xch_w + buf * 32;
+        if (gen_live) cw[lane] = make_double2(a, b);
+        __syncwarp();
         buf ^= 1;
-        return xb;
+        return cw + base;
     };
     // Z[cfg][row][col] = (zsub[..][0][b], zsub[..][1][b]).  Row g (V = Z I) and column g (dI = Z^T dV) of the active
     // configuration are walked with a running pointer: one 64-bit add per element instead of the full index product.
@@ -111,15 +133,27 @@ dps_adjoint_kernel(const BwdParams p) {
         dps_sincos(X[DPS_X_DELTA], &sd, &cd);
         double i_re, i_im;
         injection(X, par, sd, cd, i_re, i_im);
-        const double* xb = exchange(i_re, i_im);
+        const double2* xb = exchange(i_re, i_im);
         v_re = 0.0;
         v_im = 0.0;
-        const double* zp = z_cfg(cfg) + g * z_row_stride;
-        for (int j = 0; j < p.n_gen; ++j, zp += z_col_stride) {
-            const double zr = __ldg(zp), zi = __ldg(zp + zb);
-            const double jr = xb[j * 64 + lane], ji = xb[j * 64 + 32 + lane];
-            v_re += zr * jr - zi * ji;
-            v_im += zr * ji + zi * jr;
+        if (!p.z_per_sim) {
+            const double* zr_ = s_ztr + cfg * G * G + gl;
+            const double* zi_ = s_zti + cfg * G * G + gl;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const double zr = zr_[j * G], zi = zi_[j * G];
+                const double jr = xb[j].x, ji = xb[j].y;
+                v_re += zr * jr - zi * ji;
+                v_im += zr * ji + zi * jr;
+            }
+        } else {
+            const double* zp = z_cfg(cfg) + g * z_row_stride;
+            for (int j = 0; j < p.n_gen; ++j, zp += z_col_stride) {
+                const double zr = __ldg(zp), zi = __ldg(zp + zb);
+                const double jr = xb[j].x, ji = xb[j].y;
+                v_re += zr * jr - zi * ji;
+                v_im += zr * ji + zi * jr;
+            }
         }
         stage_derivatives<CTRL>(X, par, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
     };
@@ -162,9 +196,12 @@ dps_adjoint_kernel(const BwdParams p) {
             for (int k = 0; k < NS; ++k) x[k] = src[(long long)k * P];
             for (int step = k0; step < k1; ++step) {
                 if (live) {
-                    double* dst = p.scratch + (((long long)(step - k0) * p.n_gen + g) * NS) * P + s;
+                    // scratch layout [step][state][trajectory][generator]: the lanes of a warp (consecutive generators of
+                    // consecutive trajectories) touch one contiguous line per state
+                    double* dst = p.scratch + (((long long)(step - k0) * NS) * P + s) * p.n_gen + g;
+                    const long long ks = P * p.n_gen;
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) dst[(long long)k * P] = x[k];
+                    for (int k = 0; k < NS; ++k) dst[k * ks] = x[k];
                 }
                 if (step == k1 - 1) break;
                 const int cfg = cfg_of(step);
@@ -209,9 +246,10 @@ dps_adjoint_kernel(const BwdParams p) {
             const int cfg = cfg_of(step);
             double X[4][NS], sds[4], cds[4], vres[4], vims[4];
             {
-                const double* src = p.scratch + (((long long)(step - k0) * p.n_gen + g) * NS) * P + s;
+                const double* src = p.scratch + (((long long)(step - k0) * NS) * P + s) * p.n_gen + g;
+                const long long ks = P * p.n_gen;
 #pragma unroll
-                for (int k = 0; k < NS; ++k) X[0][k] = src[(long long)k * P];
+                for (int k = 0; k < NS; ++k) X[0][k] = src[k * ks];
             }
             // recorded post-step states: rec[.., step] = x_{step+1}
             if (live && rec_mask) {
@@ -254,7 +292,7 @@ dps_adjoint_kernel(const BwdParams p) {
                 double dsd, dcd, dv_re, dv_im;
                 stage_vjp<CTRL>(X[i], par, ctrl, p.fn, sds[i], cds[i], vres[i], vims[i], dk, ac, dx, gp, dsd, dcd, dv_re, dv_im);
                 // dI = Z^T dV over the generator rows ...
-                const double* xb = exchange(dv_re, dv_im);
+                const double2* xb = exchange(dv_re, dv_im);
                 double di_re = 0.0, di_im = 0.0;
                 // ... and, when the network carries a gradient, dZ[r][g] += dV_r conj(I_g): this thread owns column g of
                 // its trajectory's matrix, so the accumulation in HBM needs no atomics.  I_g is recomputed (6 flops).
@@ -265,15 +303,27 @@ dps_adjoint_kernel(const BwdParams p) {
                     gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
                 }
                 const long long gz_row = (long long)p.z_cols * 2 * P;
-                const double* zp = z_cfg(cfg) + g * z_col_stride;
-                for (int r = 0; r < p.n_gen; ++r, zp += z_row_stride) {
-                    const double zr = __ldg(zp), zi = __ldg(zp + zb);
-                    const double ar = xb[r * 64 + lane], ai = xb[r * 64 + 32 + lane];
-                    di_re += zr * ar + zi * ai;
-                    di_im += -zi * ar + zr * ai;
-                    if (ZGRAD && live) {
-                        gz[r * gz_row] += ar * own_re + ai * own_im;
-                        gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                if (!p.z_per_sim && !ZGRAD) {
+                    const double* zr_ = s_znr + cfg * G * G + gl;
+                    const double* zi_ = s_zni + cfg * G * G + gl;
+#pragma unroll
+                    for (int r = 0; r < G; ++r) {
+                        const double zr = zr_[r * G], zi = zi_[r * G];
+                        const double ar = xb[r].x, ai = xb[r].y;
+                        di_re += zr * ar + zi * ai;
+                        di_im += -zi * ar + zr * ai;
+                    }
+                } else {
+                    const double* zp = z_cfg(cfg) + g * z_col_stride;
+                    for (int r = 0; r < p.n_gen; ++r, zp += z_row_stride) {
+                        const double zr = __ldg(zp), zi = __ldg(zp + zb);
+                        const double ar = xb[r].x, ai = xb[r].y;
+                        di_re += zr * ar + zi * ai;
+                        di_im += -zi * ar + zr * ai;
+                        if (ZGRAD && live) {
+                            gz[r * gz_row] += ar * own_re + ai * own_im;
+                            gz[r * gz_row + P] += -ar * own_im + ai * own_re;
+                        }
                     }
                 }
                 // ... plus the recorded voltages of extra observed buses (last stage of the step)
@@ -316,8 +366,14 @@ dps_adjoint_kernel(const BwdParams p) {
 template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
 static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
-    const size_t smem = sizeof(double) * (G * DPS_N_SLOTS + 2 * C::GROUPS * G * 64) + sizeof(short) * G * DPS_N_SLOTS;
-    const long long spb = 32LL * C::GROUPS;
+    const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * G * DPS_N_SLOTS + sizeof(short) * G * DPS_N_SLOTS +
+                        (p.z_per_sim ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long spb = (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + spb - 1) / spb;
     dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();

@@ -17,8 +17,8 @@ struct BwdParams {
     double* g_x0;              // [n_gen][13][P]
     double* gslot;             // [n_want][P]
     double* g_zsub;            // [n_cfg][z_rows][z_cols][2][P] accumulated, or null
-    double* scratch;           // [ckpt_stride][n_gen][13][P]
-    int n_obs, z_rows, z_cols, z_per_sim, ckpt_stride, n_ckpt, n_seg;
+    double* scratch;           // [ckpt_stride][13][P][n_gen]
+    int n_obs, z_rows, z_cols, n_cfg, z_per_sim, ckpt_stride, n_ckpt, n_seg;
     int fast_par;              // plan pmode 1/3: only the DPS_N_REG_SLOTS leading slots may differ per trajectory
     int seg_step[MAX_SEG];
     int seg_cfg[MAX_SEG];
