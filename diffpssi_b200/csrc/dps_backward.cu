@@ -34,6 +34,9 @@ DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN
 #undef DPS_EXTERN
 
 static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl, int ngp, cudaStream_t stream) {
+#ifdef DPS_ONLY_G10      // kernel A/B experiment builds (tools/build_variant.sh)
+    return g_template == 10 ? launch_bwd_g<10>(p, ctrl, ngp, stream) : cudaErrorInvalidValue;
+#endif
     switch (g_template) {
         case 1: return launch_bwd_g<1>(p, ctrl, ngp, stream);
         case 2: return launch_bwd_g<2>(p, ctrl, ngp, stream);

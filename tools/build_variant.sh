@@ -11,6 +11,7 @@ for s in dps_abi dps_forward dps_forward_wide dps_network dps_backward; do
   nvcc $F -c $s.cu -o $out/obj_$name/$s.o 2> $out/obj_$name/$s.log &
 done
 nvcc $F -DDPS_G=10 -c dps_forward_inst.cu -o $out/obj_$name/g10.o 2> $out/obj_$name/g10.log &
+nvcc $F -DDPS_G=10 -c dps_backward_inst.cu -o $out/obj_$name/b10.o 2> $out/obj_$name/b10.log &
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libdps_$name.so $out/obj_$name/*.o
 grep -A2 "ILi10ELi7ELi3ELi0ELi1" $out/obj_$name/g10.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo
