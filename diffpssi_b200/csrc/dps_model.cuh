@@ -225,8 +225,8 @@ __device__ __forceinline__ double windup_gate(double state, double dx, double lo
 // (synchronous_machine.py:271-277) + differential() (synchronous_machine.py:148-172) with the controller
 // get_output()/differential() pairs it calls.  Writes f[0..12] (zero for absent controllers).
 //
-// LIM = true applies the limiter / anti-windup selects (blocks.py:145-149, 181, 241).  LIM = false is the same code
-// without them, valid when no block sits at a limit (a block inside its limits passes its input through unchanged):
+// LIM = true applies the PT1Limited clamp / anti-windup selects (blocks.py:145-149, 181).  LIM = false is the same code
+// without them, valid when no PT1Limited block sits at a limit (it then passes its state and derivative through unchanged):
 // stage_derivatives<CTRL, VOTE = true> tests the limits of all 32 lanes with one warp vote (they are functions of the
 // states only) and takes the select-free body when no lane needs them -- the common case outside fault transients.
 // Each body is one straight-line block, so the scheduler can interleave its independent chains freely.
@@ -282,10 +282,10 @@ __device__ __forceinline__ void stage_body(const double* x, const PR& par, int c
             xg = x[DPS_X_GOV_PT1]; vmin = par(DPS_S_G_VMIN); vmax = par(DPS_S_G_VMAX);
         }
         double v_pss = 0.0;
-        if (ctrl & DPS_CTRL_PSS) {
-            v_pss = o2;
-            if (limiting) v_pss = clampd(o2, -hl, hl);                               // blocks.py:241
-        }
+        // the stabiliser's output limiter is applied unconditionally (two selects): with the stock H_lim = 0.03 it
+        // saturates during most of a transient, and routing it through the vote would send 40 % of the warps down the
+        // slow body for the sake of a clamp
+        if (ctrl & DPS_CTRL_PSS) v_pss = clampd(o2, -hl, hl);                        // blocks.py:241
         if (ctrl & DPS_CTRL_AVR) {
             // SEXS.get_output(|v_bb| - v_pss), exciters.py:111-114
             // |v|: the 1e-300 floor (far below one ulp of any |v|^2 > 1e-284) replaces the zero guard of the root
@@ -338,25 +338,14 @@ __device__ __forceinline__ void stage_body(const double* x, const PR& par, int c
     alg.p_e = p_e; alg.i_d = i_d; alg.i_q = i_q; alg.v_re = v_re; alg.v_im = v_im; alg.e_fd = e_fd; alg.p_m = p_m;
 }
 
-// True when a limiter of this generator is active at state x: the stabiliser output outside +-H_lim, or a PT1Limited
-// state at / beyond one of its limits (the only situations in which the LIM selects of stage_body change a value).
+// True when a PT1Limited block of this generator sits at / beyond one of its limits at state x: the only situation in
+// which the LIM selects of stage_body change a value (the stabiliser's output clamp is always applied).
 template <class PR>
 __device__ __forceinline__ bool stage_at_limit(const double* x, const PR& par, int ctrl) {
     bool at = false;
-    if (ctrl & DPS_CTRL_PSS) {
-        const bool fed = (ctrl & DPS_CTRL_AVR) != 0;
-        const double omega = x[DPS_X_OMEGA];
-        const double w = par(DPS_S_S_INV_TW) * fma(par(DPS_S_S_KW), (fed ? omega : 0.0), -x[DPS_X_PSS_W]);
-        const double in1 = fed ? w : 0.0;
-        const double o1 = fma(par(DPS_S_S_R1), in1, par(DPS_S_S_OMR1) * x[DPS_X_PSS_LL1]);
-        const double in2 = fed ? o1 : 0.0;
-        const double o2 = fma(par(DPS_S_S_R2), in2, par(DPS_S_S_OMR2) * x[DPS_X_PSS_LL2]);
-        const double hl = par(DPS_S_S_HLIM);
-        at = (o2 < -hl) || (o2 > hl);
-    }
     if (ctrl & DPS_CTRL_AVR) {
         const double xe = x[DPS_X_AVR_PT1];
-        at = at || (xe <= par(DPS_S_A_EMIN)) || (xe >= par(DPS_S_A_EMAX));
+        at = (xe <= par(DPS_S_A_EMIN)) || (xe >= par(DPS_S_A_EMAX));
     }
     if (ctrl & DPS_CTRL_GOV) {
         const double xg = x[DPS_X_GOV_PT1];
