@@ -286,7 +286,7 @@ def main():
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             tj = json.load(f)
-        if P_total == P_GLOBAL and world == 1:
+        if P_total == P_GLOBAL and world == 1 and info['sims_per_block'] == tj.get('sims_per_block', 12):
             traffic = tj['dram_bytes_per_launch']
     except Exception:
         pass
@@ -343,7 +343,9 @@ def main():
             'config': workload_config(P_total, world),
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / peak_tf, 'traffic': traffic,
-                         'kernel': 'dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun>',
+                         'kernel': ('dps_step_pair_kernel<G=10, heun, omega recorder> (two trajectories per thread)'
+                                    if info['sims_per_block'] == 24 else
+                                    'dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun>'),
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': REC_BYTES_PER_SIM_STEP * P * T_STEPS,
                          'flops_per_sim_step': FLOPS_PER_SIM_STEP,
                          'peak_source': 'DFMA probe (dps_fp64_peak_probe) in this process; MEASURED_PEAKS.json has no fp64 entry',

@@ -178,10 +178,10 @@ int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_pe
         if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
     } else {
         fwd_geometry(plan->g_template, &th, &spb);
-        if (regs_per_thread) {
-            cudaError_t e = launch_forward(plan->base, plan->g_template, plan->cmask, plan->pmode, 0, &regs);
-            if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
-        }
+        FwdParams q = plan->base;
+        q.P = plan->last_P;                    // the specialisation depends on the batch size (pair kernel)
+        cudaError_t e = launch_forward(q, plan->g_template, plan->cmask, plan->pmode, 0, &regs, &spb);
+        if (e != cudaSuccess) { set_error("dps_plan_info: %s", cudaGetErrorString(e)); return 3; }
     }
     if (block_threads) *block_threads = th;
     if (sims_per_block) *sims_per_block = spb;
@@ -203,6 +203,7 @@ static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int st
     if (plan->topo.ckpt_stride > 0 && !ckpt) { set_error("%s: checkpoints requested but ckpt is null", who); return 1; }
     if (step_begin < 0 || step_end > plan->topo.n_steps || step_begin > step_end) { set_error("%s: bad step range [%d, %d)", who, step_begin, step_end); return 1; }
     if (step_begin == step_end) return 0;
+    plan->last_P = P;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_seg = (int)plan->seg_step.size();
     // first segment that covers step_begin

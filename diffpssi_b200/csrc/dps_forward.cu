@@ -5,9 +5,9 @@
 namespace dps {
 
 template <int G>
-cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs);
+cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs, int* spb);
 
-#define DPS_EXTERN(G) extern template cudaError_t launch_forward_g<G>(const FwdParams&, int, int, cudaStream_t, int*);
+#define DPS_EXTERN(G) extern template cudaError_t launch_forward_g<G>(const FwdParams&, int, int, cudaStream_t, int*, int*);
 DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(16)
 #undef DPS_EXTERN
 
@@ -23,20 +23,20 @@ void fwd_geometry(int g_template, int* threads, int* sims_per_block) {
     *sims_per_block = DPS_FWD_WARPS * (32 / g_template);
 }
 
-cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream, int* regs) {
+cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream, int* regs, int* spb) {
 #ifdef DPS_ONLY_G10      // kernel A/B experiment builds (tools/build_variant.sh): only the bench specialisation is linked
-    return g_template == 10 ? launch_forward_g<10>(p, cmask, pmode, stream, regs) : cudaErrorInvalidValue;
+    return g_template == 10 ? launch_forward_g<10>(p, cmask, pmode, stream, regs, spb) : cudaErrorInvalidValue;
 #else
     switch (g_template) {
-        case 1: return launch_forward_g<1>(p, cmask, pmode, stream, regs);
-        case 2: return launch_forward_g<2>(p, cmask, pmode, stream, regs);
-        case 3: return launch_forward_g<3>(p, cmask, pmode, stream, regs);
-        case 4: return launch_forward_g<4>(p, cmask, pmode, stream, regs);
-        case 5: return launch_forward_g<5>(p, cmask, pmode, stream, regs);
-        case 6: return launch_forward_g<6>(p, cmask, pmode, stream, regs);
-        case 8: return launch_forward_g<8>(p, cmask, pmode, stream, regs);
-        case 10: return launch_forward_g<10>(p, cmask, pmode, stream, regs);
-        case 16: return launch_forward_g<16>(p, cmask, pmode, stream, regs);
+        case 1: return launch_forward_g<1>(p, cmask, pmode, stream, regs, spb);
+        case 2: return launch_forward_g<2>(p, cmask, pmode, stream, regs, spb);
+        case 3: return launch_forward_g<3>(p, cmask, pmode, stream, regs, spb);
+        case 4: return launch_forward_g<4>(p, cmask, pmode, stream, regs, spb);
+        case 5: return launch_forward_g<5>(p, cmask, pmode, stream, regs, spb);
+        case 6: return launch_forward_g<6>(p, cmask, pmode, stream, regs, spb);
+        case 8: return launch_forward_g<8>(p, cmask, pmode, stream, regs, spb);
+        case 10: return launch_forward_g<10>(p, cmask, pmode, stream, regs, spb);
+        case 16: return launch_forward_g<16>(p, cmask, pmode, stream, regs, spb);
         default: return cudaErrorInvalidValue;
     }
 #endif

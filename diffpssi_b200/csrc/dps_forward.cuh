@@ -37,6 +37,7 @@
 #ifndef DPS_REC_SYNC_STEPS
 #define DPS_REC_SYNC_STEPS 16
 #endif
+#include "dps_forward_pair.cuh"
 
 namespace dps {
 
@@ -431,7 +432,12 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
 }
 
 template <int G>
-cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs) {
+cudaError_t launch_forward_g(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs, int* spb) {
+    {   // large batches of the hot configuration: two trajectories per thread (dps_forward_pair.cuh)
+        cudaError_t e;
+        if (try_pair_kernel<G>(p, cmask, pmode, stream, regs, spb, &e)) return e;
+    }
+    if (spb) *spb = FwdCfg<G>::WARPS * FwdCfg<G>::SPW;
     const int zps = (p.z_per_sim || !FwdCfg<G>::Z_SMEM) ? 1 : 0;
 #define DPS_CASE(C, M, Z)                                                                          \
     if constexpr (Z == 1 || FwdCfg<G>::Z_SMEM) {                                                   \

@@ -7,5 +7,5 @@
 #endif
 
 namespace dps {
-template cudaError_t launch_forward_g<DPS_G>(const FwdParams&, int, int, cudaStream_t, int*);
+template cudaError_t launch_forward_g<DPS_G>(const FwdParams&, int, int, cudaStream_t, int*, int*);
 }

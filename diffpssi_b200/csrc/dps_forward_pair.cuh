@@ -1,0 +1,277 @@
+// dps_forward_pair.cuh -- the stepping kernel with TWO trajectories per thread (sm_100a), a specialisation of
+// dps_step_kernel (dps_forward.cuh) for its hot configuration:
+//
+//   all three controllers on every generator with common, batch-uniform constants (plan pmode 3), network shared by the
+//   batch, Heun or Euler, regular recorder with a compile-time field mask, no extra observed buses, no checkpoints, and
+//   only the "identification" constants (1/(2H), D, the two X_d' differences, p_m0, e_fd0, v_set, bias, p_ref) differing
+//   between trajectories.
+//
+// Why: the FP64 pipe of B200 only approaches its peak when a warp offers it independent instructions back to back
+// (profiles/probe_dfma_latency_ilp.txt: one dependent chain per warp -> 66 % however many warps are resident, two -> 80 %),
+// and every non-FP64 instruction costs issue bandwidth (profiles/probe_issue_mix.txt).  One stage evaluation is a long
+// dependency chain; two trajectories in one thread give the scheduler a second, fully independent chain to interleave,
+// and everything that does not depend on the trajectory -- the Z row (20 LDS per stage), the generator's batch-uniform
+// machine constants, the controller and trigonometric constants -- is loaded once for both.
+//
+// Same equations (dps_model.cuh), same exchange scheme (warp-private shared-memory lines), same recorder layout and the
+// same periodic block barrier as dps_step_kernel; results are bit-identical to it (tests/test_cuda_parity.py).  254
+// registers, 8 warps per SM of 6 trajectories each: a "wave" is 7104 trajectories, so the dispatcher (try_pair_kernel,
+// called from launch_forward_g) only uses it from 16 384 trajectories per GPU on.  Measured (IEEE-39, Heun, T = 2000):
+//   trajectories   8192    16384   32768   49152   65536
+//   pair kernel    5.49    8.97    17.61   24.61   33.22  ms      FP64 pipe 77 % busy, 218 instructions per trajectory-stage
+//   dps_step_kernel 4.89   9.43    17.62   25.81   34.05  ms      FP64 pipe 73.5 %, 245 instructions
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include "dps_internal.h"
+#include "dps_model.cuh"
+
+namespace dps {
+
+// per-trajectory register constants of the pair kernel (dps_lean_slot) vs batch-uniform shared-memory reads
+__host__ __device__ constexpr bool dps_pair_reg_slot(int slot) {
+    return slot == DPS_S_INV_2H || slot == DPS_S_D || slot == DPS_S_XD_XDT || slot == DPS_S_XDT_XDST ||
+           slot == DPS_S_PM0 || slot == DPS_S_EFD0 || slot == DPS_S_A_VSET || slot == DPS_S_A_BIAS || slot == DPS_S_G_PREF;
+}
+
+struct ParamPair {
+    const double* pm;        // registers, [DPS_N_REG_SLOTS]: only dps_pair_reg_slot entries are per trajectory
+    const double* sh;        // registers, [DPS_N_REG_SLOTS]: the generator's batch-uniform machine constants (shared by both)
+    const double* cp;        // kernel parameter block, [DPS_N_SLOTS]
+    __device__ __forceinline__ double operator()(int slot) const {
+        return (slot >= DPS_N_REG_SLOTS) ? cp[slot] : (dps_pair_reg_slot(slot) ? pm[slot] : sh[slot]);
+    }
+};
+
+template <int G>
+struct PairCfg {
+    static constexpr int SPW = 32 / G;             // trajectory PAIRS per warp
+    static constexpr int WARPS = 4;
+    static constexpr int THREADS = 32 * WARPS;
+};
+
+template <int G, int SOLVER, int RMASK>
+__global__ void __launch_bounds__(PairCfg<G>::THREADS, 2)
+dps_step_pair_kernel(const FwdParams p) {
+    using C = PairCfg<G>;
+    constexpr int SPW = C::SPW, NS = DPS_N_STATES, CM = 7;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_zr = reinterpret_cast<double*>(smem_raw);                               // [n_cfg][col j][row g]
+    double* s_zi = s_zr + p.n_cfg * G * G;
+    double2* s_cur = reinterpret_cast<double2*>(s_zi + p.n_cfg * G * G);              // [WARPS][2 buffers][2 trajectories][32]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sl = lane / G;
+    const int gl = lane - sl * G;
+    const int base = ((sl < SPW) ? sl : SPW - 1) * G;
+    const bool gen_live = (sl < SPW) && (gl < p.n_gen);
+    const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
+    const long long P = p.P;
+    const long long sim0 = (((long long)blockIdx.x * C::WARPS + warp) * SPW + sl) * 2;   // this thread: sim0, sim0 + 1
+    bool live[2];
+    long long s[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        live[u] = gen_live && (sim0 + u < P);
+        s[u] = (sim0 + u < P) ? sim0 + u : (P - 1);
+    }
+
+    for (int i = threadIdx.x; i < C::WARPS * 128; i += blockDim.x) s_cur[i] = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
+        const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
+        const bool ok = row < p.n_gen && col < p.n_gen;
+        const double* e = p.zsub + (((long long)cfg * p.z_rows + (ok ? row : 0)) * p.z_cols + (ok ? col : 0)) * 2;
+        s_zr[i] = ok ? e[0] : 0.0;
+        s_zi[i] = ok ? e[1] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- constants ----------------------------------------------------------------------------------------------------
+    double sh[DPS_N_REG_SLOTS], pm[2][DPS_N_REG_SLOTS];
+#pragma unroll
+    for (int k = 0; k < DPS_N_REG_SLOTS; ++k) {
+        const int vi = p.slot_vary[g * DPS_N_SLOTS + k];
+        const double uni = __ldg(p.upar + g * DPS_N_SLOTS + k);
+        sh[k] = uni;                                                   // read only where !dps_pair_reg_slot(k)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) pm[u][k] = (vi >= 0) ? __ldg(p.vpar + (long long)vi * P + s[u]) : uni;
+    }
+    const ParamPair par[2] = {{pm[0], sh, p.cpar}, {pm[1], sh, p.cpar}};
+
+    double x[2][NS];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const double* src = p.x0 + (long long)g * DPS_N_STATES * P + s[u];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) x[u][k] = src[(long long)k * P];
+    }
+
+    int seg = 0;
+    while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= p.step_begin) ++seg;
+    int cfg = p.seg_cfg[seg];
+    int next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
+    const double* zcol_r = s_zr + cfg * G * G + gl;
+    const double* zcol_i = s_zi + cfg * G * G + gl;
+
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    // recorder: one running pointer per recorded field; the thread's two trajectories are adjacent in every row
+    constexpr int N_RUN = __builtin_popcount((unsigned)RMASK & 0x1FFFu);
+    const long long rec_cs = (long long)p.n_steps * P;
+    double* rec_run[N_RUN > 0 ? N_RUN : 1];
+    {
+        int q = 0;
+#pragma unroll
+        for (int k = 0; k < DPS_N_STATES; ++k)
+            if ((RMASK >> k) & 1)
+                rec_run[q++] = p.rec + ((long long)g + p.rec_fbase[k]) * rec_cs + (long long)p.step_begin * P + sim0;
+    }
+    int buf = 0;
+    double2* cur_w = s_cur + warp * 128;
+
+    // one stage evaluation of both trajectories
+    auto eval = [&](double (*X)[NS], double (*f)[NS]) {
+        double sd[2], cd[2];
+        double2* cw = cur_w + buf * 64;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            dps_sincos(X[u][DPS_X_DELTA], &sd[u], &cd[u]);
+            double i_re, i_im;
+            injection(X[u], par[u], sd[u], cd[u], i_re, i_im);
+            if (gen_live) cw[u * 32 + lane] = make_double2(i_re, i_im);
+        }
+        __syncwarp();
+        buf ^= 1;
+        const double2* cg0 = cw + base;
+        const double2* cg1 = cw + 32 + base;
+        // V = Z I for both trajectories: every Z element is loaded once
+        double vr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, vi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const double zre = zcol_r[j * G], zim = zcol_i[j * G];
+            const double2 a = cg0[j], b = cg1[j];
+            vr[0][0] = fma(zre, a.x, vr[0][0]);
+            vr[0][1] = fma(-zim, a.y, vr[0][1]);
+            vi[0][0] = fma(zre, a.y, vi[0][0]);
+            vi[0][1] = fma(zim, a.x, vi[0][1]);
+            vr[1][0] = fma(zre, b.x, vr[1][0]);
+            vr[1][1] = fma(-zim, b.y, vr[1][1]);
+            vi[1][0] = fma(zre, b.y, vi[1][0]);
+            vi[1][1] = fma(zim, b.x, vi[1][1]);
+        }
+        // limiter vote over both trajectories of all lanes (see stage_derivatives in dps_model.cuh)
+        const bool at = stage_at_limit(X[0], par[0], CM) || stage_at_limit(X[1], par[1], CM);
+        Algebraics alg;
+        if (__any_sync(0xffffffffu, at)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                stage_body<true, true>(X[u], par[u], CM, p.fn, sd[u], cd[u], vr[u][0] + vr[u][1], vi[u][0] + vi[u][1], f[u], alg);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                stage_body<true, false>(X[u], par[u], CM, p.fn, sd[u], cd[u], vr[u][0] + vr[u][1], vi[u][0] + vi[u][1], f[u], alg);
+        }
+    };
+
+    for (int step = p.step_begin; step < p.step_end; ++step) {
+#if DPS_REC_SYNC_STEPS > 0
+        if ((step & (DPS_REC_SYNC_STEPS - 1)) == 0) __syncthreads();      // see dps_step_kernel
+#endif
+        if (step == next_change) {
+            ++seg;
+            cfg = p.seg_cfg[seg];
+            next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
+            zcol_r = s_zr + cfg * G * G + gl;
+            zcol_i = s_zi + cfg * G * G + gl;
+        }
+        double f[2][NS];
+        if (SOLVER == DPS_EULER) {
+            eval(x, f);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < NS; ++k) x[u][k] = x[u][k] + f[u][k] * dt;
+        } else {
+            double xt[2][NS];
+            eval(x, f);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < NS; ++k) { xt[u][k] = fma(f[u][k], dt, x[u][k]); x[u][k] = fma(f[u][k], hdt, x[u][k]); }
+            eval(xt, f);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < NS; ++k) x[u][k] = fma(f[u][k], hdt, x[u][k]);
+        }
+        {
+            int q = 0;
+#pragma unroll
+            for (int k = 0; k < DPS_N_STATES; ++k)
+                if ((RMASK >> k) & 1) {
+                    if (live[0]) dps_rec_store(rec_run[q], x[0][k]);
+                    if (live[1]) dps_rec_store(rec_run[q] + 1, x[1][k]);
+                    rec_run[q] += P;
+                    ++q;
+                }
+        }
+    }
+
+    if (p.x_final != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (live[u]) {
+                double* dst = p.x_final + (long long)g * DPS_N_STATES * P + s[u];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) dst[(long long)k * P] = x[u][k];
+            }
+    }
+}
+
+// Can this launch use the pair kernel?  (see the header comment)
+template <int G>
+static bool pair_kernel_applies(const FwdParams& p, int cmask, int pmode, long long min_sims) {
+    if (cmask != 7 || pmode != 3 || p.z_per_sim || p.ckpt_stride > 0 || p.n_obs != p.n_gen) return false;
+    if (p.solver != DPS_HEUN && p.solver != DPS_EULER) return false;
+    if (!p.rec_regular || p.rec_umask != 0x1u || p.P < min_sims) return false;
+    for (int g = 0; g < p.n_gen; ++g)
+        for (int k = 0; k < DPS_N_REG_SLOTS; ++k)
+            if (!dps_pair_reg_slot(k) && p.slot_vary[g * DPS_N_SLOTS + k] >= 0) return false;
+    return true;
+}
+
+template <int G, int SOLVER>
+static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, int* regs) {
+    using C = PairCfg<G>;
+    auto kern = dps_step_pair_kernel<G, SOLVER, 0x1>;
+    if (regs) {
+        cudaFuncAttributes a;
+        cudaError_t e = cudaFuncGetAttributes(&a, kern);
+        if (e != cudaSuccess) return e;
+        *regs = a.numRegs;
+        return cudaSuccess;
+    }
+    const size_t smem = sizeof(double) * p.n_cfg * G * G * 2 + sizeof(double2) * C::WARPS * 128;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long sims_per_block = (long long)C::WARPS * C::SPW * 2;
+    const long long blocks = (p.P + sims_per_block - 1) / sims_per_block;
+    kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Hook called by launch_forward_g (dps_forward.cuh): true when the pair kernel took the launch.
+template <int G>
+bool try_pair_kernel(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs, int* spb, cudaError_t* err) {
+    const char* env = getenv("DPS_PAIR_MIN_SIMS");                  // experiments / tests: 0 = always, huge = never
+    const long long min_sims = env ? atoll(env) : 16384;
+    if (!pair_kernel_applies<G>(p, cmask, pmode, min_sims)) return false;
+    if (spb) *spb = PairCfg<G>::WARPS * PairCfg<G>::SPW * 2;
+    *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN>(p, stream, regs)
+                                  : launch_pair_solver<G, DPS_EULER>(p, stream, regs);
+    return true;
+}
+
+}  // namespace dps

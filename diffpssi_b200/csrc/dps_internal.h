@@ -70,8 +70,9 @@ struct WideParams {
 int fwd_template_g(int n_gen);
 void fwd_geometry(int g_template, int* threads, int* sims_per_block);
 #ifdef __CUDACC__
+// regs_query / sims_per_block_query non-null: no launch, report the kernel that WOULD run for p (incl. p.P)
 cudaError_t launch_forward(const FwdParams& p, int g_template, int cmask, int pmode, cudaStream_t stream,
-                           int* regs_query);
+                           int* regs_query, int* sims_per_block_query = nullptr);
 cudaError_t launch_forward_wide(const WideParams& p, int cmask, int pmode, cudaStream_t stream, int* regs_query,
                                 int* threads, int* sims_per_block);
 #endif

@@ -17,4 +17,5 @@ struct dps_plan {
     bool wide;                            // more than MAX_G generators: dps_step_wide_kernel
     dps::WideParams wbase;
     dps::FwdParams base;                       // everything that does not depend on the call
+    mutable long long last_P = 0;              // batch size of the latest forward call (dps_plan_info reports its kernel)
 };

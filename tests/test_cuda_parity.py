@@ -249,6 +249,33 @@ def test_recorder_specialisations_agree():
     assert torch.equal(out['omega'], out['irregular'])
 
 
+def test_pair_kernel_matches_single_trajectory_kernel(monkeypatch):
+    """dps_step_pair_kernel (two trajectories per thread, used for large batches of the all-controllers / shared-network /
+    omega-recorder configuration) against dps_step_kernel on the same ragged batch, and against the C oracle."""
+    from diffpssi_b200 import grids
+    rng = np.random.RandomState(21)
+    P = 77                                                   # ragged: 12 full warps of 6 trajectories + 5
+    ov = {}
+    for g, (h, xdt) in grids.GENERATOR_NOMINALS['ieee39'].items():
+        ov[(g, 'h')] = h * rng.uniform(0.8, 1.25, P)
+        ov[(g, 'd')] = rng.uniform(0.0, 2.0, P)
+        ov[(g, 'x_d_t')] = xdt * rng.uniform(0.9, 1.1, P)
+    out, regs = {}, {}
+    for name, min_sims in (('pair', '0'), ('single', '999999999')):
+        monkeypatch.setenv('DPS_PAIR_MIN_SIMS', min_sims)
+        sim = _ieee39_sim(P, ov, T=600)
+        _, res = sim.run()
+        out[name] = res.clone()
+        regs[name] = sim.last_plan.info()['regs_per_thread']
+    assert regs['pair'] != regs['single']                    # the two launches really used different kernels
+    assert float((out['pair'] - out['single']).abs().max()) < 1e-12
+    monkeypatch.setenv('DPS_PAIR_MIN_SIMS', '0')
+    sim = _ieee39_sim(P, ov, T=600)
+    _, res = sim.run()
+    ref = helpers.run_oracle_for(sim, sim.last_init, rec_channels=[(0, g, 0) for g in range(10)], full=False)
+    assert np.abs(res.cpu().numpy() - ref['rec'].transpose(2, 1, 0)).max() < TOL
+
+
 def test_full_size_k2a_4096():
     """BASELINE config 2 (K2A, 4096 trajectories, 2000 Heun steps, per-sim H/D/X_d' in the stable range): 24 sampled
     rows re-run as a small batch are bit-identical, and match the C oracle to 1e-9."""

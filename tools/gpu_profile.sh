@@ -13,5 +13,5 @@ CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
 if [ "${LAUNCHES:-0}" = "1" ]; then
   $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dps_ -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 fi
-$CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dps_step_kernel -s 1 -c 1 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dps_step_ -s 1 -c 1 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
