@@ -272,6 +272,11 @@ def test_pair_kernel_matches_single_trajectory_kernel(monkeypatch):
     monkeypatch.setenv('DPS_PAIR_MIN_SIMS', '0')
     sim = _ieee39_sim(P, ov, T=600)
     _, res = sim.run()
+    # step ranges (dps_forward_range: state carried through x_out, recorder pointers offset by step_begin)
+    sim.reset()
+    host = torch.empty((10, 600, P), dtype=torch.float64).pin_memory()
+    _, streamed = sim.run(host_out=host, stream_chunks=5)
+    assert torch.equal(streamed, res.cpu())
     ref = helpers.run_oracle_for(sim, sim.last_init, rec_channels=[(0, g, 0) for g in range(10)], full=False)
     assert np.abs(res.cpu().numpy() - ref['rec'].transpose(2, 1, 0)).max() < TOL
 
