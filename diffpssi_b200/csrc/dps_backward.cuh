@@ -256,7 +256,13 @@ dps_adjoint_kernel(const BwdParams p) {
                 const double* gr = p.grad_rec + (long long)step * P + sim;
 #pragma unroll
                 for (int k = 0; k < NS; ++k)
-                    if (rec_mask & (1u << k)) lam[k] += gr[ch[k] * cs];
+                    if (rec_mask & (1u << k)) {
+                        const double* e = gr + ch[k] * cs;
+                        lam[k] += *e;
+                        // the sweep walks the steps backwards: fetch the previous step's cotangent now, it is consumed
+                        // a whole step later (this load sat on the critical path with full HBM latency)
+                        if (step > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(e - P));
+                    }
             }
             // stage inputs and their voltages
 #pragma unroll
