@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from diffpssi_b200 import Pss
 from tests import helpers
 from tests.test_gradients_host import CASES, loss_of
 
@@ -88,3 +89,37 @@ def test_shared_network_parameter_gradient():
     lm = float(loss_of_run(*build(0.23 - h, False)[:2]))
     fd = (lp - lm) / (2 * h)
     assert abs(fd) > 0 and abs(fd - g) / abs(fd) < 1e-5, (fd, g)
+
+
+def test_identification_loop_reduces_the_loss():
+    """A miniature of the reference's parameter identification (examples/models/ibb_model/ibb_opt.py,
+    optimization_lib/ps_optimization.py:178-212): the target trajectory comes from the nominal H, every simulation of the
+    batch starts from a wrong H, and a few gradient steps on the per-sim H (gradients from dps_backward through the
+    prologue graph) must pull every trajectory towards the target."""
+    P = 16
+    grid = helpers.load_grid('ibb')
+
+    def run(h_values, leaf=None):
+        sim = Pss(parallel_sims=P, sim_time=2.0, time_step=0.005, solver='heun', grid_data=grid, verbose=False)
+        sim.add_sc_event(1.0, 1.05, 'Bus 1')
+        gen = sim.get_generator_by_name('Gen 1')
+        gen.h = leaf if leaf is not None else torch.tensor(h_values.reshape(P, 1), dtype=torch.complex128, device='cuda')
+        sim.set_record_channels(['Gen 1.omega'])
+        _, res = sim.run()
+        return res
+
+    with torch.no_grad():
+        target = run(np.full(P, 3.5))[:1]                                  # nominal H = 3.5 s
+    h = torch.tensor(np.linspace(2.0, 6.0, P).reshape(P, 1), dtype=torch.complex128, device='cuda', requires_grad=True)
+    opt = torch.optim.Adam([h], lr=0.15)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = ((run(None, leaf=h) - target) ** 2).mean(dim=(1, 2))
+        losses.append(loss.detach().clone())
+        loss.sum().backward()
+        opt.step()
+    first, last = losses[0], losses[-1]
+    off = (h.detach().real.reshape(-1) - 3.5).abs() > 0.3                  # sims that did not start next to the optimum
+    assert bool((last[off] < 0.5 * first[off]).all()), (first, last)
+    assert float((h.detach().real.reshape(-1) - 3.5).abs().mean()) < float(np.abs(np.linspace(2.0, 6.0, P) - 3.5).mean())
