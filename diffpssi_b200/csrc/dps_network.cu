@@ -22,7 +22,71 @@ __global__ void dps_network_reduce_kernel(const ReduceParams p) {
     network_reduce_one(p, b);
 }
 
+// Network shared by the batch (Bz == 1): the same update, one block, threads spread over the matrix ELEMENTS.  (One
+// thread walking the whole matrix with dependent global loads took 50 us -- 1 % of a bench step at 8192 trajectories
+// per GPU.)  Every element of a rank-1 update only needs old values of its own row / the faulted row, so each step is
+// "everybody loads, barrier, everybody stores".
+__global__ void __launch_bounds__(256) dps_network_reduce_shared_kernel(const ReduceParams p) {
+    const int rows = p.n_obs + p.m_max, cols = p.n_gen + p.m_max;
+    const int n_el = rows * cols;
+    for (int cfg = 0; cfg < p.n_cfg; ++cfg) {
+        double* W = p.zsub + (long long)cfg * n_el * 2;
+        const int m = p.cfg_n[cfg];
+        // gather rows {observed, faulted} x columns {generators, faulted}
+        for (int e = threadIdx.x; e < n_el; e += blockDim.x) {
+            const int r = e / cols, c = e - r * cols;
+            const int rb = (r < p.n_obs) ? p.obs_bus[r] : ((r - p.n_obs) < m ? p.cfg_bus[cfg][r - p.n_obs] : -1);
+            const int cb = (c < p.n_gen) ? p.gen_bus[c] : ((c - p.n_gen) < m ? p.cfg_bus[cfg][c - p.n_gen] : -1);
+            double re = 0.0, im = 0.0;
+            if (rb >= 0 && cb >= 0) {
+                re = p.z_re[(long long)rb * p.n_bus + cb];
+                im = p.z_im[(long long)rb * p.n_bus + cb];
+            }
+            W[2 * e] = re;
+            W[2 * e + 1] = im;
+        }
+        __syncthreads();
+        for (int k = 0; k < m; ++k) {
+            const int fb = p.cfg_bus[cfg][k];
+            const int rk = p.n_obs + k, ck = p.n_gen + k;
+            // f = c / (1 + c Z_bb), c = y_fault - Y_bb   (every thread computes it from the same old values)
+            const double c_re = p.y_fault - p.yd_re[fb], c_im = -p.yd_im[fb];
+            const double zbb_re = W[2 * (rk * cols + ck)], zbb_im = W[2 * (rk * cols + ck) + 1];
+            const double den_re = 1.0 + (c_re * zbb_re - c_im * zbb_im);
+            const double den_im = c_re * zbb_im + c_im * zbb_re;
+            const double dn = den_re * den_re + den_im * den_im;
+            const double f_re = (c_re * den_re + c_im * den_im) / dn;
+            const double f_im = (c_im * den_re - c_re * den_im) / dn;
+            // this thread's elements (at most a few: strided over the block); old values first ...
+            constexpr int MAX_OWN = 8;
+            double nre[MAX_OWN], nim[MAX_OWN];
+            int own = 0;
+            for (int e = threadIdx.x; e < n_el && own < MAX_OWN; e += blockDim.x, ++own) {
+                const int r = e / cols, c = e - r * cols;
+                const double a_re = W[2 * (r * cols + ck)], a_im = W[2 * (r * cols + ck) + 1];       // Z[r][b]
+                const double b_re = W[2 * (rk * cols + c)], b_im = W[2 * (rk * cols + c) + 1];       // Z[b][c]
+                const double t_re = f_re * a_re - f_im * a_im, t_im = f_re * a_im + f_im * a_re;
+                nre[own] = W[2 * e] - (t_re * b_re - t_im * b_im);
+                nim[own] = W[2 * e + 1] - (t_re * b_im + t_im * b_re);
+            }
+            __syncthreads();
+            // ... then the new ones
+            own = 0;
+            for (int e = threadIdx.x; e < n_el && own < MAX_OWN; e += blockDim.x, ++own) {
+                W[2 * e] = nre[own];
+                W[2 * e + 1] = nim[own];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream) {
+    const int rows = p.n_obs + p.m_max, cols = p.n_gen + p.m_max;
+    if (p.Bz == 1 && rows * cols <= 256 * 8) {
+        dps_network_reduce_shared_kernel<<<1, 256, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     const int threads = 128;
     const long long blocks = (p.Bz + threads - 1) / threads;
     dps_network_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p);
