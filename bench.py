@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- sim-steps/s of the Pss.run() time loop, IEEE 39-bus / 10 generators (SEXS+TGOV1+STAB1), Heun, fp64.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sims P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sims P] [--variant generic]
 
 One bench "step" = one pass of the hot path over the whole synthetic batch: fault re-reduction + the persistent
 stepping kernel integrating T = 2000 time steps (10 s at dt = 5 ms, 100 ms three-phase fault at load bus B16) of
@@ -11,10 +11,11 @@ loop, initialisation excluded exactly like the reference's own timer (simulator.
 
 JSON line (rank 0): value = device-timed loop with inputs resident in HBM; e2e = the same metric through the public
 API (pinned host parameter batch -> H2D -> Pss.run() incl. load flow/initialisation -> recorder D2H into pinned host
-memory); roofline = algorithmic fp64 flops of the stepping kernel against a DFMA peak measured in the same process;
-cpu_baseline = the C oracle (oracle/dps_oracle.c, OpenMP over all host cores) on a bounded sample of the same workload.
-``--impl reference`` times that CPU restatement alone (the reference is pure Python and does not travel to the GPU box;
-DESIGN.md section 7).
+memory); roofline = algorithmic fp64 flops of the stepping kernel against max(DFMA, DMMA) peak probes run in the same
+process; cpu_baseline = the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build()) with its numpy and
+torch-CPU backends on the box's host cores on a bounded sample of the same workload, its torch-CUDA path on this GPU as
+the incumbent GPU implementation, and the C restatement (oracle/dps_oracle.c, OpenMP) next to them.
+``--impl reference`` times the reference itself (the faster of its two CPU backends).
 """
 import argparse
 import json
@@ -54,15 +55,35 @@ def parameter_batch(P_global, seed=0):
     return batch
 
 
-def build_sim(P, device, rows, batch_host):
+def generic_grid():
+    """--variant generic: the same IEEE-39 system with DISTINCT controller settings on every machine (gains and time
+    constants spread by a few per cent), so the stepper cannot use its common-constant (constant-bank) specialisation
+    nor the two-trajectories-per-thread kernel -- the path a user with a hand-tuned grid gets."""
+    from diffpssi_b200 import grids
+    grid = grids.ieee39()
+    for key, sub, cols in (('avr', 'SEXS', ('K', 'T_a', 'T_b', 'T_e')), ('gov', 'TGOV1', ('R', 'T_1', 'T_3')),
+                           ('pss', 'STAB1', ('K', 'T', 'T_1', 'T_3'))):
+        table = grid[key][sub]
+        head = table[0]
+        for i, row in enumerate(table[1:]):
+            for c in cols:
+                row[head.index(c)] = row[head.index(c)] * (1.0 + 0.01 * (i + 1))
+    return grid
+
+
+def build_sim(P, device, rows, batch_host, variant='headline'):
     """IEEE-39 simulation for rows [rows) of the global parameter draw; parameters handed in as [P,1] complex128
     tensors exactly like a reference user would (ibb_opt.py:48-57)."""
     import torch
     from diffpssi_b200 import Pss, grids
-    sim = Pss(parallel_sims=P, sim_time=T_STEPS * DT, time_step=DT, solver='heun', grid_data=grids.ieee39(),
-              verbose=False, device=device)
+    sim = Pss(parallel_sims=P, sim_time=T_STEPS * DT, time_step=DT, solver='heun',
+              grid_data=generic_grid() if variant == 'generic' else grids.ieee39(), verbose=False, device=device)
     sim.add_sc_event(*FAULT)
-    sim.set_record_function(lambda s: [s.busses[29 + i].models[0].omega.real for i in range(10)])
+    if variant == 'generic':          # omega AND delta of every generator: the run-time recorder mask, 160 B per sim-step
+        sim.set_record_function(lambda s: [s.busses[29 + i].models[0].omega.real for i in range(10)] +
+                                          [s.busses[29 + i].models[0].delta.real for i in range(10)])
+    else:
+        sim.set_record_function(lambda s: [s.busses[29 + i].models[0].omega.real for i in range(10)])
     assert len(sim.time) == T_STEPS
     set_parameters(sim, batch_host, rows, device)
     return sim
@@ -126,7 +147,7 @@ class ClockSampler(object):
                 'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_baseline(sample_sims, batch, threads=None):
+def c_port_baseline(sample_sims, batch, threads=None):
     """The C oracle (literal CPU restatement of the reference loop) on the first ``sample_sims`` rows of the workload.
     Loop only; the prologue is excluded like on the GPU side."""
     from oracle import adapter, oracle
@@ -143,31 +164,120 @@ def cpu_baseline(sample_sims, batch, threads=None):
     return sample_sims * T_STEPS / dt, dt, out['rec']
 
 
+REF_RUNNER = os.path.join(ROOT, 'baseline', 'run_reference.py')
+REF_SIMS = 1024          # the reference's throughput saturates by 1-4 k sims; its initialize() is O(P^2)
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'diffpssi'))
+
+
+def run_reference_backend(backend, sims, steps, repeats=1, warmup=0, timeout=900):
+    """One process of baseline/run_reference.py (the unmodified reference, loop-only timing) -> its JSON dict.
+    The sample covers ``steps`` consecutive steps of the run with the workload's own fault-step fraction (1 %)."""
+    cmd = [sys.executable, REF_RUNNER, '--backend', backend, '--sims', str(sims), '--steps', str(steps),
+           '--fault-steps', str(max(1, round(steps * 20 / T_STEPS))), '--repeats', str(repeats), '--warmup', str(warmup)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {'unavailable': 'timed out after %d s' % timeout}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            return json.loads(ln)
+    return {'unavailable': 'rc %d: %s' % (r.returncode, r.stderr.strip()[-300:])}
+
+
+def cpu_baseline(batch, with_cuda_incumbent, port_sample):
+    """The baselines BASELINE.json north_star names, timed beside the GPU arm on the box's own host cores: the reference's
+    numpy and torch-CPU backends (and its torch-CUDA path on this GPU), plus the C port.  ``value`` is the faster of the two
+    real CPU backends (kind 'reference'); without baseline/_ref it falls back to the port (kind 'port')."""
+    cores = os.cpu_count() or 1
+    backends = {}
+    v, dt_s, _ = c_port_baseline(port_sample, batch, cores)
+    backends['c_port'] = {'sim_steps_per_s': v, 'threads': cores, 'kind': 'port',
+                          'sample': '%d trajectories x %d steps, %.1f s of oracle/dps_oracle.c with OpenMP' % (port_sample, T_STEPS, dt_s)}
+    best = None
+    if reference_available():
+        todo = ['numpy', 'torch'] + (['torch-cuda'] if with_cuda_incumbent else [])
+        for be in todo:
+            d = run_reference_backend(be, REF_SIMS, 300)
+            key = {'numpy': 'reference_numpy', 'torch': 'reference_torch_cpu', 'torch-cuda': 'reference_torch_cuda'}[be]
+            if 'unavailable' in d:
+                backends[key] = d
+                continue
+            backends[key] = {'sim_steps_per_s': d['sim_steps_per_s'], 'threads': d['threads'], 'kind': 'reference',
+                             'device': d['device'], 'loop_s': d['loop_s'], 'initialize_s': d['initialize_s'],
+                             'sample': '%d trajectories x %d steps incl. %d fault steps, loop only (simulator.py:507,548-550)'
+                                       % (d['parallel_sims'], d['steps'], d['fault_steps'])}
+            if be != 'torch-cuda' and (best is None or d['sim_steps_per_s'] > best[1]['sim_steps_per_s']):
+                best = (key, d)
+    if best is not None:
+        key, d = best
+        return {'value': d['sim_steps_per_s'], 'unit': 'sim-steps/s', 'cores': cores, 'kind': 'reference',
+                'backend': key, 'threads': d['threads'],
+                'sample': 'unmodified reference (%s backend), %d trajectories x %d steps of the same workload (rows 0..%d of the '
+                          'seed-0 draw), loop only' % (d['backend'], d['parallel_sims'], d['steps'], d['parallel_sims'] - 1),
+                'backends': backends}
+    return {'value': v, 'unit': 'sim-steps/s', 'cores': cores, 'kind': 'port', 'backend': 'c_port',
+            'sample': backends['c_port']['sample'] + ' (baseline/_ref not installed: reference backends not timed)',
+            'backends': backends}
+
+
 def run_reference_arm(args, out=sys.stdout):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python/numpy/torch and
-    is not present on the GPU box, so this arm times its C restatement (oracle, kind 'port') with every host thread."""
+    """--impl reference: the reference's own CPU implementation of the path, unmodified (baseline/_ref), through its public
+    API: each bench step is one ``run()`` of 1024 trajectories x 100 steps of the workload (1 fault step = the workload's
+    1 % fault fraction), loop-only like the reference's own timer.  The faster of its numpy / torch-CPU backends on this
+    box is used (probed first); the other one and the C port are reported beside it.  Falls back to the C port (kind
+    'port') when baseline/_ref is absent."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     batch = parameter_batch(P_GLOBAL)
-    # size the per-step sample for ~2 s of CPU work: ~40 ms per trajectory per core (measured), bounded
-    sample = int(min(P_GLOBAL, max(cores * 48, 64)))
-    times = []
-    for i in range(args.warmup + args.steps):
-        v, dt, _ = cpu_baseline(sample, batch, cores)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = sample * T_STEPS / (ms * 1e-3)
+    others = {}
+    kind, backend, threads = 'port', 'c_port', cores
+    if reference_available():
+        probe = {be: run_reference_backend(be, REF_SIMS, 40) for be in ('numpy', 'torch')}
+        ok = {be: d for be, d in probe.items() if 'unavailable' not in d}
+        for be, d in probe.items():
+            others['probe_' + be] = d.get('sim_steps_per_s', d.get('unavailable'))
+        if ok:
+            backend = max(ok, key=lambda be: ok[be]['sim_steps_per_s'])
+            d = run_reference_backend(backend, REF_SIMS, 100, repeats=args.steps, warmup=args.warmup, timeout=1500)
+            if 'unavailable' not in d:
+                kind, threads = 'reference', d['threads']
+                sample, ms = REF_SIMS, 1e3 * d['loop_s']
+                steps_per_run = d['steps']
+                note = ('unmodified reference, %s backend: %d trajectories x %d steps per bench step, loop only; '
+                        'initialize() (%.1f s per run, O(P^2)) excluded' % (backend, sample, steps_per_run, d['initialize_s']))
+            else:
+                others['run_error'] = d['unavailable']
+    if kind == 'port':
+        sample = int(min(P_GLOBAL, max(cores * 48, 64)))
+        times = []
+        for i in range(args.warmup + args.steps):
+            v, dt, _ = c_port_baseline(sample, batch, cores)
+            if i >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        steps_per_run = T_STEPS
+        note = 'CPU restatement of the reference loop (oracle/dps_oracle.c) on a bounded sample'
+    else:
+        v, dt, _ = c_port_baseline(int(min(P_GLOBAL, max(cores * 48, 64))), batch, cores)
+        others['c_port'] = v
+    value = sample * steps_per_run / (ms * 1e-3)
+    cfg = workload_config(sample, args.gpus, note=note)
+    cfg['steps_per_run'] = steps_per_run
+    cfg['l2'] = 'n/a (CPU arm)'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'sim-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(sample, args.gpus, note='CPU restatement of the reference loop on a bounded sample'),
-        'cpu_baseline': {'value': value, 'unit': 'sim-steps/s', 'cores': cores, 'kind': 'port',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': value, 'unit': 'sim-steps/s', 'cores': cores, 'threads': threads, 'kind': kind,
+                         'backend': backend,
                          'sample': '%d trajectories x %d steps per bench step (rows 0..%d of the seed-0 draw)'
-                                   % (sample, T_STEPS, sample - 1)},
+                                   % (sample, steps_per_run, sample - 1),
+                         'others_sim_steps_per_s': others},
         'e2e': {'value': value, 'unit': 'sim-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -175,13 +285,26 @@ def run_reference_arm(args, out=sys.stdout):
     out.flush()
 
 
-def workload_config(P, n_gpus, note=None):
+def kernel_label(info, variant):
+    if variant == 'generic':
+        return ('dps_step_kernel<G=10, all controllers, per-generator controller constants from shared memory, heun, '
+                'run-time recorder mask> (%d registers)' % info['regs_per_thread'])
+    if info['sims_per_block'] % 6 == 0 and info['regs_per_thread'] > 170:
+        return 'dps_step_pair_kernel<G=10, heun, omega recorder> (two trajectories per thread, %d registers)' % info['regs_per_thread']
+    return ('dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun> (%d registers)'
+            % info['regs_per_thread'])
+
+
+def workload_config(P, n_gpus, note=None, variant='headline', n_rec=10):
     cfg = {'workload': 'IEEE 39-bus New-England, 10 generators each with SEXS+TGOV1+STAB1 (130 states/sim), Heun, '
                        'dt=5 ms, T=2000 steps, 100 ms three-phase fault at bus B16, recorder = omega of 10 generators',
            'parallel_sims': P, 'steps_per_run': T_STEPS, 'solver': 'heun', 'parallelism': 'dp%d (rows of one seed-0 draw)' % n_gpus,
            'parameters': "per-sim H, X_d' ~ U(0.5,2) x nominal and D ~ U(0,2) for every generator",
            'l2': 'recorder output (%.1f GB per bench step per GPU) far exceeds the 126 MB L2, so inputs are evicted '
-                 'between timed iterations' % (P / n_gpus * T_STEPS * REC_BYTES_PER_SIM_STEP / 1e9)}
+                 'between timed iterations' % (P / n_gpus * T_STEPS * 8 * n_rec / 1e9)}
+    if variant == 'generic':
+        cfg['variant'] = ('generic: controller gains / time constants differ per generator (no common-constant kernel '
+                          'specialisation, no two-trajectory kernel), recorder = omega and delta of the 10 generators')
     if note:
         cfg['note'] = note
     return cfg
@@ -195,6 +318,8 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--sims', type=int, default=P_GLOBAL, help='global parallel_sims (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--variant', default='headline', choices=('headline', 'generic'),
+                    help="'generic': distinct controller constants per generator + omega/delta recorder (no specialised kernel)")
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     # the JSON line must be the only thing on stdout: libraries (NCCL prints its version with printf) get stderr
@@ -233,7 +358,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: value / roofline ----------------------------------------------------------
-    sim = build_sim(P, dev, (lo, hi), batch)
+    sim = build_sim(P, dev, (lo, hi), batch, args.variant)
     prep = sim.prepare()
     n_rec = len(prep.topo['rec'])
     rec = torch.empty((n_rec, T_STEPS, P), dtype=torch.float64, device=dev)
@@ -272,7 +397,9 @@ def main():
     info = prep.plan.info()
 
     # fp64 roofline denominator, measured here (MEASURED_PEAKS.json has no fp64 entry)
-    peak_tf, _ = engine.fp64_peak_probe(8192)
+    dfma_tf, _ = engine.fp64_peak_probe(8192)
+    dmma_tf, _ = engine.fp64_dmma_probe(4096)
+    peak_tf = max(dfma_tf, dmma_tf)
     achieved_tf = FLOPS_PER_SIM_STEP * P * T_STEPS / (kernel_ms * 1e-3) / 1e12
     peaks = {}
     try:
@@ -290,7 +417,8 @@ def main():
             traffic = tj['dram_bytes_per_launch']
     except Exception:
         pass
-    rec_gbs = REC_BYTES_PER_SIM_STEP * P * T_STEPS / (kernel_ms * 1e-3) / 1e9
+    rec_bytes = 8 * n_rec                                     # recorder bytes per sim-step (80 for the headline recorder)
+    rec_gbs = rec_bytes * P * T_STEPS / (kernel_ms * 1e-3) / 1e9
 
     # ---------------- end-to-end arm: public API with host buffers ----------------------------------------------------
     e2e = None
@@ -328,29 +456,27 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
         cores = os.cpu_count() or 1
-        sample = int(min(P_total, max(cores * 192, 256)))
-        v, dt_s, cpu_rec = cpu_baseline(sample, batch, cores)
-        cpu = {'value': v, 'unit': 'sim-steps/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d trajectories x %d steps (rows 0..%d of the same seed-0 draw), %.1f s of C oracle with '
-                         'OpenMP on %d threads' % (sample, T_STEPS, sample - 1, dt_s, cores)}
+        cpu = cpu_baseline(batch, with_cuda_incumbent=True, port_sample=int(min(P_total, max(cores * 192, 256))))
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'sim-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(P_total, world),
+            'config': workload_config(P_total, world, variant=args.variant, n_rec=n_rec),
             'roofline': {'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved_tf / peak_tf, 'traffic': traffic,
-                         'kernel': ('dps_step_pair_kernel<G=10, heun, omega recorder> (two trajectories per thread)'
-                                    if info['sims_per_block'] == 24 else
-                                    'dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun>'),
-                         'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': REC_BYTES_PER_SIM_STEP * P * T_STEPS,
+                         'kernel': kernel_label(info, args.variant),
+                         'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': rec_bytes * P * T_STEPS,
                          'flops_per_sim_step': FLOPS_PER_SIM_STEP,
-                         'peak_source': 'DFMA probe (dps_fp64_peak_probe) in this process; MEASURED_PEAKS.json has no fp64 entry',
+                         'peak_source': 'max(DFMA probe, DMMA probe) run in this process (same FP64 pipe; nominal 148 SM x 64 lanes x '
+                                        '2 x 1.965 GHz = 37.2); MEASURED_PEAKS.json has no fp64 entry and the profiling guide '
+                                        'states no fp64 fallback',
+                         'peak_dfma_probe': dfma_tf, 'peak_dmma_probe': dmma_tf,
                          'hbm': {'achieved': rec_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': rec_gbs / hbm_peak,
-                                 'bytes_per_sim_step': REC_BYTES_PER_SIM_STEP}},
+                                 'bytes_per_sim_step': rec_bytes}},
             'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': 2 * args.steps,
             'kernel': info, 'finite_fraction': finite, 'checksum': checksum, 'clocks': clocks,

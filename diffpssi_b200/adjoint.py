@@ -26,18 +26,20 @@ def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec, want_z=False):
     dev = upar.device
     want = topo.get('want') or [0] * (G * engine.N_SLOTS)
     n_want = sum(want)
-    g_x0 = torch.empty((G, engine.N_STATES, P), dtype=torch.float64, device=dev)
-    gslot = torch.empty((max(n_want, 1), P), dtype=torch.float64, device=dev)
+    # zero-filled: a run of zero steps writes neither (the library returns before launching anything)
+    g_x0 = torch.zeros((G, engine.N_STATES, P), dtype=torch.float64, device=dev)
+    gslot = torch.zeros((max(n_want, 1), P), dtype=torch.float64, device=dev)
     ws_bytes = int(lib.dps_workspace_bytes(plan.handle, P))
     ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
     a_want = (ctypes.c_uint8 * len(want))(*want)
     # dL/dZsub is accumulated per trajectory ([n_cfg, rows, cols, 2, P], zero-initialised by the caller)
     gz = torch.zeros(tuple(zsub.shape[:4]) + (P,), dtype=torch.float64, device=dev) if want_z else None
-    rc = lib.dps_backward(plan.handle, P, engine._ptr(upar.detach().contiguous()),
-                          engine._ptr(vpar.detach().contiguous()) if vpar is not None else None,
-                          engine._ptr(zsub), engine._ptr(ckpt), engine._ptr(g_rec), None, a_want,
-                          engine._ptr(g_x0), engine._ptr(gslot), engine._ptr(gz),
-                          ctypes.c_void_p(ws.data_ptr()), ws_bytes, engine._stream())
+    with engine._on_device_of(ckpt):
+        rc = lib.dps_backward(plan.handle, P, engine._ptr(upar.detach().contiguous()),
+                              engine._ptr(vpar.detach().contiguous()) if vpar is not None else None,
+                              engine._ptr(zsub), engine._ptr(ckpt), engine._ptr(g_rec), None, a_want,
+                              engine._ptr(g_x0), engine._ptr(gslot), engine._ptr(gz),
+                              ctypes.c_void_p(ws.data_ptr()), ws_bytes, engine._stream(ckpt))
     engine._check(lib, rc, 'dps_backward')
     g_upar = torch.zeros_like(upar)
     g_vpar = torch.zeros_like(vpar) if vpar is not None else None

@@ -52,7 +52,10 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
     if (t->n_steps < 0 || !(t->dt > 0.0)) { set_error("dps_plan_create: bad n_steps/dt"); return 1; }
     if (t->n_obs < t->n_gen || t->n_obs - t->n_gen > MAX_EXTRA_OBS) { set_error("dps_plan_create: n_obs out of range"); return 1; }
     if (t->z_rows < t->n_obs || t->z_cols < t->n_gen) { set_error("dps_plan_create: z_rows/z_cols smaller than n_obs/n_gen"); return 1; }
-    if (t->n_cfg < 1) { set_error("dps_plan_create: n_cfg must be >= 1"); return 1; }
+    if (t->n_cfg < 1 || t->n_cfg > RED_MAX_CFG) { set_error("dps_plan_create: n_cfg %d out of range (1..%d)", t->n_cfg, RED_MAX_CFG); return 1; }
+    if (!t->ctrl || !t->slot_vary || (t->n_steps > 0 && !t->step_cfg) || (t->n_rec > 0 && !t->rec)) {
+        set_error("dps_plan_create: null ctrl / slot_vary / step_cfg / rec pointer"); return 1;
+    }
     if (t->n_rec < 0 || t->n_rec > 32000) { set_error("dps_plan_create: n_rec out of range"); return 1; }
 
     dps_plan* pl = new dps_plan();
@@ -79,7 +82,7 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
     pl->any_vary = false;
     for (int g = 0; g < t->n_gen; ++g) pl->any_ctrl |= (pl->ctrl[g] != 0);
     for (int v : pl->slot_vary) {
-        if (v >= t->n_vary) { set_error("dps_plan_create: slot_vary entry %d >= n_vary %d", v, t->n_vary); delete pl; return 1; }
+        if (v >= t->n_vary || v < -1) { set_error("dps_plan_create: slot_vary entry %d outside -1..n_vary-1 (n_vary %d)", v, t->n_vary); delete pl; return 1; }
         pl->any_vary |= (v >= 0);
     }
     pl->cmask = pl->ctrl[0];
@@ -292,6 +295,13 @@ int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds) {
     if (!tflops || !milliseconds || iters < 1) { set_error("dps_fp64_peak_probe: bad argument"); return 1; }
     cudaError_t e = run_fp64_probe(iters, tflops, milliseconds);
     if (e != cudaSuccess) { set_error("dps_fp64_peak_probe: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+int dps_fp64_dmma_probe(int32_t iters, double* tflops, double* milliseconds) {
+    if (!tflops || !milliseconds || iters < 1) { set_error("dps_fp64_dmma_probe: bad argument"); return 1; }
+    cudaError_t e = run_fp64_dmma_probe(iters, tflops, milliseconds);
+    if (e != cudaSuccess) { set_error("dps_fp64_dmma_probe: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }
 

@@ -14,7 +14,7 @@ namespace dps {
 constexpr int MAX_G = 16;            // generators handled by the warp-exchange stepper (dps_forward.cuh)
 constexpr int MAX_GW = 128;          // generators handled by the wide stepper (dps_forward_wide.cuh)
 constexpr int MAX_SEG = 48;          // network-configuration change points per launch
-constexpr int MAX_EXTRA_OBS = 24;    // recorded non-generator buses
+constexpr int MAX_EXTRA_OBS = 64;    // recorded non-generator buses (every bus of IEEE-39 can be recorded)
 
 // Kernel parameter block (passed by value -> constant bank).
 struct FwdParams {
@@ -95,6 +95,7 @@ struct ReduceParams {
 cudaError_t launch_network_reduce_params(const ReduceParams& p, cudaStream_t stream);
 
 cudaError_t run_fp64_probe(int iters, double* tflops, double* ms);
+cudaError_t run_fp64_dmma_probe(int iters, double* tflops, double* ms);
 cudaError_t launch_math_probe(long long n, const double* a, const double* b, double* out, cudaStream_t stream);
 #endif
 

@@ -110,6 +110,25 @@ __global__ void __launch_bounds__(256) dps_fp64_probe_kernel(double* out, int it
     if (s == 12345.678) out[0] = s;      // never true: keeps the chains alive
 }
 
+// FP64 MMA probe (mma.sync.m8n8k4.f64, SASS DMMA): 8 independent accumulator pairs per warp.  On B200 the MMA shares the
+// FP64 pipe with DFMA (profiles/probe_dmma_vs_dfma.txt) but issues 256 FMAs per warp instruction, so it gets closer to the
+// pipe's nominal rate than a DFMA stream does; bench.py reports max(DFMA, DMMA) as the fp64 roofline denominator.
+__global__ void __launch_bounds__(256) dps_fp64_dmma_probe_kernel(double* out, int iters, double a, double b) {
+    double m0[8], m1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m0[i] = threadIdx.x * 1e-3; m1[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(m0[i]), "+d"(m1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += m0[i] + m1[i];
+    if (s == 12345.678) out[0] = s;      // never true: keeps the accumulators alive
+}
+
 // device math self-test: out[0..4][n] = sin(a), cos(a), a/b, sqrt(|a|), 1/b with the kernels' own primitives
 __global__ void dps_math_probe_kernel(long long n, const double* a, const double* b, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,6 +144,42 @@ __global__ void dps_math_probe_kernel(long long n, const double* a, const double
 
 cudaError_t launch_math_probe(long long n, const double* a, const double* b, double* out, cudaStream_t stream) {
     dps_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, a, b, out);
+    return cudaGetLastError();
+}
+
+cudaError_t run_fp64_dmma_probe(int iters, double* tflops, double* ms_out) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    double* d_out = nullptr;
+    e = cudaMalloc(&d_out, sizeof(double));      // probe only (measurement helper, not the data path)
+    if (e != cudaSuccess) return e;
+    const int blocks = sms * 4, threads = 256;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    dps_fp64_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters / 8 + 1, 0.999, 1e-3);     // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0);
+        dps_fp64_dmma_probe_kernel<<<blocks, threads>>>(d_out, iters, 0.999, 1e-3);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return e;
+    // one m8n8k4 MMA = 8*8*4 FMAs = 512 flops per warp instruction; 8 of them per iteration
+    const double flops = 512.0 * 8.0 * (double)iters * (double)blocks * (double)(threads / 32);
+    *tflops = flops / (best * 1e-3) / 1e12;
+    *ms_out = best;
     return cudaGetLastError();
 }
 

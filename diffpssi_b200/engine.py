@@ -18,12 +18,12 @@ N_SLOTS = 42
 N_FIELDS = 20
 MAX_G = 16          # warp-exchange stepper
 MAX_GW = 128        # wide stepper
-MAX_EXTRA_OBS = 24
+MAX_EXTRA_OBS = 64
 MAX_CFG = 16
 MAX_FAULT = 8
 
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes',
-           'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_math_probe', 'dps_plan_info',
+           'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_fp64_dmma_probe', 'dps_math_probe', 'dps_plan_info',
            'dps_last_error', 'dps_abi_version')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
@@ -85,6 +85,7 @@ def load_library(path=None):
                                  ctypes.c_size_t, vp]
     lib.dps_math_probe.argtypes = [i64, vp, vp, vp, vp]
     lib.dps_fp64_peak_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+    lib.dps_fp64_dmma_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     lib.dps_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     if lib.dps_abi_version() != ABI_VERSION:
         raise EngineError('libdps_b200.so has ABI %d, python side expects %d' % (lib.dps_abi_version(), ABI_VERSION))
@@ -108,8 +109,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(ref=None):
+    """Current torch stream of the device that holds ``ref`` (default: the current device)."""
+    dev = ref.device if ref is not None else None
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _on_device_of(t):
+    """Context that makes the device of tensor ``t`` current for the duration of a C-ABI call: the library launches on
+    the *current* device, so a simulation built with ``device='cuda:1'`` while device 0 is current would otherwise run
+    its kernels on GPU 0 with GPU 1 pointers."""
+    if t is None or not t.is_cuda:
+        raise EngineError('engine buffers must live on a CUDA device; there is no CPU fallback')
+    return torch.cuda.device(t.device)
 
 
 def require_cuda():
@@ -163,14 +175,16 @@ class Plan(object):
 
     def forward(self, P, x0, upar, vpar, zsub, rec, x_final=None, ckpt=None):
         require_cuda()
-        _check(self.lib, self.lib.dps_forward(self.handle, P, _ptr(x0), _ptr(upar), _ptr(vpar), _ptr(zsub),
-                                              _ptr(rec), _ptr(x_final), _ptr(ckpt), _stream()), 'dps_forward')
+        with _on_device_of(x0):
+            _check(self.lib, self.lib.dps_forward(self.handle, P, _ptr(x0), _ptr(upar), _ptr(vpar), _ptr(zsub),
+                                                  _ptr(rec), _ptr(x_final), _ptr(ckpt), _stream(x0)), 'dps_forward')
 
     def forward_range(self, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt=None):
         require_cuda()
-        _check(self.lib, self.lib.dps_forward_range(self.handle, P, step_begin, step_end, _ptr(x_in), _ptr(upar),
-                                                    _ptr(vpar), _ptr(zsub), _ptr(rec), _ptr(x_out), _ptr(ckpt),
-                                                    _stream()), 'dps_forward_range')
+        with _on_device_of(x_in):
+            _check(self.lib, self.lib.dps_forward_range(self.handle, P, step_begin, step_end, _ptr(x_in), _ptr(upar),
+                                                        _ptr(vpar), _ptr(zsub), _ptr(rec), _ptr(x_out), _ptr(ckpt),
+                                                        _stream(x_in)), 'dps_forward_range')
 
 
 def network_reduce(z_re, z_im, yd_re, yd_im, obs_bus, gen_bus, cfg_sets, y_fault, zsub):
@@ -188,9 +202,10 @@ def network_reduce(z_re, z_im, yd_re, yd_im, obs_bus, gen_bus, cfg_sets, y_fault
     a_gen = (i32 * len(gen_bus))(*gen_bus)
     a_ptr = (i32 * len(ptr))(*ptr)
     a_bus = (i32 * max(len(flat), 1))(*flat)
-    _check(lib, lib.dps_network_reduce(Bz, n_bus, _ptr(z_re), _ptr(z_im), _ptr(yd_re), _ptr(yd_im),
-                                       len(obs_bus), a_obs, len(gen_bus), a_gen, len(cfg_sets), a_ptr, a_bus,
-                                       float(y_fault), _ptr(zsub), _stream()), 'dps_network_reduce')
+    with _on_device_of(zsub):
+        _check(lib, lib.dps_network_reduce(Bz, n_bus, _ptr(z_re), _ptr(z_im), _ptr(yd_re), _ptr(yd_im),
+                                           len(obs_bus), a_obs, len(gen_bus), a_gen, len(cfg_sets), a_ptr, a_bus,
+                                           float(y_fault), _ptr(zsub), _stream(zsub)), 'dps_network_reduce')
 
 
 def math_probe(a, b):
@@ -198,7 +213,8 @@ def math_probe(a, b):
     require_cuda()
     lib = load_library()
     out = torch.empty((5, a.numel()), dtype=torch.float64, device=a.device)
-    _check(lib, lib.dps_math_probe(a.numel(), _ptr(a), _ptr(b), _ptr(out), _stream()), 'dps_math_probe')
+    with _on_device_of(a):
+        _check(lib, lib.dps_math_probe(a.numel(), _ptr(a), _ptr(b), _ptr(out), _stream(a)), 'dps_math_probe')
     return out
 
 
@@ -207,4 +223,13 @@ def fp64_peak_probe(iters=4096):
     lib = load_library()
     tf, ms = ctypes.c_double(), ctypes.c_double()
     _check(lib, lib.dps_fp64_peak_probe(iters, ctypes.byref(tf), ctypes.byref(ms)), 'dps_fp64_peak_probe')
+    return tf.value, ms.value
+
+
+def fp64_dmma_probe(iters=4096):
+    """FP64 tensor-core (DMMA) throughput of the current device in TFLOP/s -> (tflops, ms)."""
+    require_cuda()
+    lib = load_library()
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    _check(lib, lib.dps_fp64_dmma_probe(iters, ctypes.byref(tf), ctypes.byref(ms)), 'dps_fp64_dmma_probe')
     return tf.value, ms.value

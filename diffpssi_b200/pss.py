@@ -35,7 +35,7 @@ def _tabular(value):
 class PowerSystemSimulation(object):
 
     def __init__(self, time_step, sim_time, parallel_sims, solver, grid_data=None, verbose=True,
-                 backend=None, device=None, ckpt_stride=32):
+                 backend=None, device=None, ckpt_stride=32, prologue_device=None):
         backend = backend or BACKEND
         if backend != 'cuda':
             raise ValueError("diffpssi_b200 implements backend='cuda' only (got %r); the numpy/torch backends are "
@@ -44,6 +44,10 @@ class PowerSystemSimulation(object):
         if device is None:
             device = 'cuda' if torch.cuda.is_available() else 'cpu'      # cpu: host-side logic only (tests)
         self.device = str(device)
+        # Extension: where the once-per-run prologue (load flow, model initialisation, inv(Y)) is evaluated.  Default: the
+        # run device.  'cpu' keeps the ~10^3 tiny tensor ops of the prologue off the GPU (no launch latency -- the better
+        # choice for small batches) and uploads the packed kernel inputs; autograd still reaches the user's leaves.
+        self.prologue_device = str(prologue_device) if prologue_device is not None else self.device
         self.time = np.arange(0, sim_time, time_step)                       # simulator.py:78
         self.time_step = time_step
         self.busses, self.non_slack_busses, self.bus_idxs = [], [], {}
@@ -121,7 +125,7 @@ class PowerSystemSimulation(object):
         self.busses[self.bus_idxs[slack_bus]].lf_type = 'SL'
 
     def _par(self, model):
-        model.enable_parallel_simulation(self.parallel_sims, self.device)
+        model.enable_parallel_simulation(self.parallel_sims, self.prologue_device)
         return model
 
     def add_bus(self, bus_model):
@@ -183,13 +187,23 @@ class PowerSystemSimulation(object):
         self.record_channels = list(names)
         self.record_func = None
 
+    def invalidate_caches(self):
+        """Drop every memoised prologue result (load flow, inv(Y_dyn), derived model constants, packed tables, event
+        schedule).  The memoisation keys tensors on identity + version counter; a write through ``.data``
+        (``p.data += ...``, as the reference's own optimiser does, optimization_lib/optimizers.py:83) bumps neither, so
+        after such a write on a tensor that does NOT require grad call this before the next run().  (Tensors that require
+        grad always bypass the caches.)"""
+        for k in ('_prologue_cache', '_pack_cache', '_schedule_cache'):
+            self.__dict__.pop(k, None)
+        self._uniform_cache = {}
+
     def reset(self):
         """simulator.py:485-495 / static_models.py:189-197: bus voltages back to the last model's set point (or 1.0),
         cached matrices dropped.  The next run() redoes load flow and initialisation from scratch."""
         P = self.parallel_sims
         if getattr(self, '_flat_start', None) is None:
             # one shared (never written) tensor, so that the prologue's memoisation sees the same input after every reset
-            self._flat_start = torch.ones((P, 1), dtype=torch.complex128, device=self.device)
+            self._flat_start = torch.ones((P, 1), dtype=torch.complex128, device=self.prologue_device)
         for bus in self.busses:
             v = getattr(bus.models[-1], 'v_soll', None) if bus.models else None
             bus.voltage = v if v is not None else self._flat_start
@@ -201,13 +215,13 @@ class PowerSystemSimulation(object):
     # ------------------------------------------------------------------------------------------------------------
     def initialize(self):
         """Load flow, model initialisation, Z = inv(Y_dyn), initial bus voltages (simulator.py:438-450)."""
-        init = prologue.initialize(self, self.device)
+        init = prologue.initialize(self, self.prologue_device)
         self.inverse_dynamic_y_matrix = init.Z0
         P = self.parallel_sims
         cur = prologue.initial_injections(init)                                   # [B,G]
         B = max(cur.shape[0], init.Z0.shape[0])
         n = len(self.busses)
-        inj = torch.zeros((B, n), dtype=torch.complex128, device=self.device)
+        inj = torch.zeros((B, n), dtype=torch.complex128, device=self.prologue_device)
         cols = [inj[:, i] for i in range(n)]
         for gi, b in enumerate(init.gen_bus):
             cols[b] = cols[b] + cur[:, gi]
@@ -230,7 +244,7 @@ class PowerSystemSimulation(object):
         Returns a :class:`PreparedRun` whose ``launch()`` enqueues the kernels (used by bench.py to time the loop
         alone, as the reference's own timer does -- simulator.py:507, 548-550)."""
         init = self.initialize()
-        P, dev = self.parallel_sims, self.device
+        P, dev, pdev = self.parallel_sims, self.device, self.prologue_device
         rplan = self._trace_recorder(init)
         net_grad = torch.is_grad_enabled() and (init.Z0.requires_grad or init.Ydiag.requires_grad)
         needs_grad = net_grad or (torch.is_grad_enabled() and (
@@ -239,7 +253,7 @@ class PowerSystemSimulation(object):
         topo, extras = planning.build_topology(self, init, rplan.channel_keys, self.solver,
                                                self.ckpt_stride if needs_grad else 0)
         x0 = planning.canonical_x0(init, P)
-        upar, vpar, slot_vary = planning.pack_slots(init, P, dev, self.__dict__.setdefault('_pack_cache', {}))
+        upar, vpar, slot_vary = planning.pack_slots(init, P, pdev, self.__dict__.setdefault('_pack_cache', {}))
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
@@ -250,8 +264,13 @@ class PowerSystemSimulation(object):
         with torch.no_grad():
             z_re, z_im = planning.split_complex_batch_last(init.Z0)
             yd_re, yd_im = planning.split_complex_batch_last(init.Ydiag)
+            if pdev != dev:                              # prologue evaluated elsewhere: upload the packed kernel inputs
+                z_re, z_im, yd_re, yd_im = (t.to(dev) for t in (z_re, z_im, yd_re, yd_im))
             zsub = torch.empty((topo['n_cfg'], topo['z_rows'], topo['z_cols'], 2, z_re.shape[-1]),
                                dtype=torch.float64, device=dev)
+        if pdev != dev:                                  # .to() is differentiable: gradients flow back to the leaves
+            x0, upar = x0.to(dev), upar.to(dev)
+            vpar = None if vpar is None else vpar.to(dev)
         return PreparedRun(self, init, rplan, plan, topo, extras, x0, upar, vpar, (z_re, z_im, yd_re, yd_im), zsub)
 
     def run(self, host_out=None, stream_chunks=8):
@@ -321,6 +340,7 @@ class PreparedRun(object):
             # a gradient flows into the network: the fault re-reduction becomes part of the torch graph
             zsub = planning.network_reduce_torch(self.init.Z0, self.init.Ydiag, self.extras['obs_bus'],
                                                  self.extras['gen_bus'], self.extras['cfg_sets'], self.extras['m_max'])
+            zsub = zsub.to(self.sim.device)
         else:
             with torch.no_grad():
                 self.reduce_network()
@@ -346,9 +366,12 @@ class PreparedRun(object):
         No autograd through this path."""
         engine.require_cuda()
         sim, topo = self.sim, self.topo
-        if torch.is_grad_enabled() and (self.x0.requires_grad or self.upar.requires_grad or
-                                        (self.vpar is not None and self.vpar.requires_grad)):
-            raise NotImplementedError('gradients through parameter events / streamed runs are not supported')
+        if torch.is_grad_enabled() and (topo.get('ckpt_stride', 0) > 0 or topo.get('want_z') or self.x0.requires_grad or
+                                        self.upar.requires_grad or (self.vpar is not None and self.vpar.requires_grad)):
+            # ckpt_stride > 0 <=> prepare() saw a tensor requiring grad (a model parameter, or a network parameter that
+            # reaches Z0 / Ydiag); ranges carry no autograd graph, so refuse instead of returning a detached result
+            raise NotImplementedError('gradients through parameter events / streamed runs are not supported: wrap run() '
+                                      'in torch.no_grad() or drop requires_grad')
         P, T, dev = sim.parallel_sims, topo['n_steps'], sim.device
         cuts = {0, T}
         when = {}
@@ -375,9 +398,10 @@ class PreparedRun(object):
                     for ev in when[k0]:
                         setattr(ev.model, ev.param_name, ev.value)
                         ev.handled = True
-                    slots = prologue.refresh_loop_slots(sim, self.init, dev)
+                    slots = prologue.refresh_loop_slots(sim, self.init, sim.prologue_device)
                     saved, self.init.slots = self.init.slots, slots
-                    upar, vpar, slot_vary = planning.pack_slots(self.init, P, dev)
+                    upar, vpar, slot_vary = planning.pack_slots(self.init, P, sim.prologue_device)
+                    upar, vpar = upar.to(dev), None if vpar is None else vpar.to(dev)
                     t2 = dict(topo, slot_vary=slot_vary, n_vary=0 if vpar is None else vpar.shape[0], ckpt_stride=0,
                               want=None)
                     t2['common_ctrl'] = planning.common_controller_constants(self.init, upar, slot_vary)

@@ -22,6 +22,11 @@ def shard_range(P_global, world_size=None, rank=None):
     """Rows [lo, hi) of the global batch owned by ``rank`` (contiguous, sizes differ by at most one)."""
     world_size = world_size if world_size is not None else get_world_size()
     rank = rank if rank is not None else get_rank()
+    if P_global < world_size:
+        # a rank with zero rows cannot build a simulation, would raise before the first collective and leave the other
+        # ranks hanging in it: refuse on every rank, up front
+        raise ValueError('parallel_sims=%d cannot be sharded over %d ranks (every rank needs at least one trajectory)'
+                         % (P_global, world_size))
     return rank * P_global // world_size, (rank + 1) * P_global // world_size
 
 

@@ -204,6 +204,10 @@ int dps_backward(const dps_plan* plan, int64_t P,
  * (MEASURED_PEAKS.json has no fp64 entry). */
 int dps_fp64_peak_probe(int32_t iters, double* tflops, double* milliseconds);
 
+/* Same measurement with the FP64 tensor-core instruction (mma.sync.m8n8k4.f64, SASS DMMA; 512 flops per warp
+ * instruction).  On B200 it shares the FP64 pipe with DFMA; bench.py uses max(DFMA, DMMA) as the roofline peak. */
+int dps_fp64_dmma_probe(int32_t iters, double* tflops, double* milliseconds);
+
 /* Test helper: evaluates the kernels' own branch-free math primitives on the device,
  * out[0..4][n] = sin(a), cos(a), a/b, sqrt(|a|), 1/b  (a, b, out: device arrays). */
 int dps_math_probe(int64_t n, const double* a, const double* b, double* out, void* stream);

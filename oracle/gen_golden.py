@@ -305,6 +305,103 @@ def _network_grad_cases(sel, one, rng):
         ['G%d.omega' % g for g in (1, 2, 3, 4)] + ['G1.e_q_st', 'G3.e_d_st'], True)
 
 
+def headline_cases(sel):
+    """Live reference outputs on the BASELINE configurations the bench times (task 1): the builder-authored
+    IEEE 39-bus and tiled grids (diffpssi_b200/grids.py, written in the reference's dict schema so that the unmodified
+    reference loads them), at full run length."""
+    from diffpssi_b200 import grids
+    import bench
+
+    def dump_grid(name, grid):
+        with open(os.path.join(GOLD, 'grids', name + '.json'), 'w') as f:
+            json.dump(grid, f)
+
+    # --- config 3 grid, nominal parameters, full 2000 Heun steps, the bench's fault
+    name = 'ieee39_heun'
+    events = [tuple(bench.FAULT)]
+    if not sel or any(s in name for s in sel):
+        dump_grid('ieee39', grids.ieee39())
+        sim, _ = rh.build(grids.ieee39(), 1, 'heun', DT, bench.T_STEPS * DT, events)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        save_case(name, t, rec, names, snap, events, 'heun', stride=10)
+    # --- the first rows of the bench's own seed-0 parameter draw (H, X_d' ~ U(0.5,2) x nominal, D ~ U(0,2))
+    name = 'ieee39_batch_heun'
+    if not sel or any(s in name for s in sel):
+        dump_grid('ieee39', grids.ieee39())
+        P = 4
+        batch = bench.parameter_batch(bench.P_GLOBAL)
+        ov = {('gen', g, attr): arr[:P].copy() for (g, attr), arr in batch.items()}
+        sim, _ = rh.build(grids.ieee39(), P, 'heun', DT, bench.T_STEPS * DT, events, ov)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        save_case(name, t, rec, names, snap, events, 'heun', extra, stride=10)
+    # --- config 5 family: tiled grid, RK4, per-sim H / X_d', fault at a load bus
+    for name, n_cells, P, T in (('tiled20_rk4', 20, 2, 400), ('tiled100_rk4', 100, 1, 300)):
+        if sel and not any(s in name for s in sel):
+            continue
+        grid = grids.tiled(n_cells)
+        dump_grid('tiled%d' % n_cells, grid)
+        rng = np.random.RandomState(50 + n_cells)
+        ov = {}
+        for c in range(n_cells):
+            ov[('gen', 'M%d' % c, 'h')] = (6.5 if c % 2 == 0 else 6.175) * rng.uniform(0.8, 1.25, P)
+            ov[('gen', 'M%d' % c, 'x_d_t')] = 0.3 * rng.uniform(0.9, 1.1, P)
+        events5 = [(0.25, 0.35, 'A3')]
+        sim, _ = rh.build(grid, P, 'rk4', DT, T * DT, events5, ov)
+        t, rec, names, snap, _ = rh.run_full(sim)
+        # generator states/algebraics of every machine, bus voltages of the first two cells and the faulted neighbourhood
+        keep = [i for i, n in enumerate(names) if not n.startswith('bus:') or n.split('.')[0][4:] in
+                ('G0', 'H0', 'A0', 'B0', 'X0', 'A3', 'H3', 'X3', 'X%d' % (n_cells - 1))]
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        save_case(name, t, rec[:, :, keep], [names[i] for i in keep], snap, events5, 'rk4', extra, stride=10)
+
+
+def ident_range_grad_case(sel):
+    """BASELINE config 4 as the reference itself would run it (examples/models/ibb_model/ibb_opt.py:48-57,
+    optimization_lib/ps_optimization.py:176-212): IBB, Heun, the full 10 s, per-sim H / D / X_d' leaves drawn from the
+    0.5x..2x identification range, loss = per-sim MSE of (omega, e_q'', e_d'') against the reference's own golden
+    trajectory (tests/integration/data/ibb_model.npy), gradients from ``loss.sum().backward()`` (``p.grad.real``)."""
+    import torch
+    name = 'grad_ibb_range_heun'
+    if sel and not any(s in name for s in sel):
+        return
+    rng = np.random.RandomState(4)
+    P = 8
+    ov = {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.5, 2.0, P),
+          ('gen', 'Gen 1', 'd'): rng.uniform(0.0, 2.0, P),
+          ('gen', 'Gen 1', 'x_d_t'): 0.3 * rng.uniform(0.5, 2.0, P)}
+    grid = rh.load_example_grid(*GRIDS['ibb'])
+    events = [(1, 1.05, 'Bus 1')]
+    chans = ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st']
+    sim, leaves = rh.build(grid, P, 'heun', DT, 10, events, ov, requires_grad=True)
+    t, rec, names, snap, rec_t = rh.run_full(sim)
+    idx = [names.index(c) for c in chans]
+    target = torch.tensor(np.load(os.path.join(rh.REFERENCE_ROOT, 'tests', 'integration', 'data', 'ibb_model.npy')))
+    out = rec_t[:, :, idx]
+    loss = ((out.real - target[None]) ** 2).mean(dim=(1, 2))
+    loss.sum().backward()
+    extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+    extra.update({'grad/' + '|'.join(k): v.grad.real.numpy().reshape(-1).copy() for k, v in leaves.items()})
+    extra['loss'] = loss.detach().numpy()
+    extra['loss_channels'] = np.array(chans)
+    extra['target2d'] = target.numpy()
+    # finite-difference cross-check of every leaf (rows are independent: perturb all rows at once)
+    for k0 in ov:
+        h = 1e-6 * np.abs(ov[k0]).max()
+        lp = []
+        for sgn in (+1, -1):
+            ov2 = dict(ov)
+            ov2[k0] = ov[k0] + sgn * h
+            s2, _ = rh.build(grid, P, 'heun', DT, 10, events, ov2)
+            _, _, n2, _, r2 = rh.run_full(s2)
+            lp.append(((r2[:, :, idx].real - target[None]) ** 2).mean(dim=(1, 2)).numpy())
+        fd = (lp[0] - lp[1]) / (2 * h)
+        g = extra['grad/' + '|'.join(k0)]
+        print('   FD check on %s: max rel diff %.2e (scale %.2e)' % ('|'.join(k0), np.abs(fd - g).max() / np.abs(g).max(), np.abs(g).max()))
+        extra['fd/' + '|'.join(k0)] = fd
+    save_case(name, t, rec, names, snap, events, 'heun', extra, stride=20)
+
+
 def main():
     sel = sys.argv[1:]
     os.makedirs(os.path.join(GOLD, 'grids'), exist_ok=True)
@@ -319,6 +416,8 @@ def main():
     batch_cases(sel)
     param_event_cases(sel)
     grad_cases(sel)
+    headline_cases(sel)
+    ident_range_grad_case(sel)
 
 
 if __name__ == '__main__':

@@ -7,7 +7,7 @@ import torch
 
 from diffpssi_b200 import Pss
 from tests import helpers
-from tests.test_gradients_host import CASES, loss_of
+from tests.test_gradients_host import CASES, loss_of, assert_gradients_match
 
 pytestmark = pytest.mark.gpu
 
@@ -22,11 +22,7 @@ def test_adjoint_matches_reference_autograd(case, grid, stride):
     loss = loss_of(result.cpu(), gold, names)
     assert np.allclose(loss.detach().numpy(), gold['loss'], rtol=1e-9, atol=0)
     loss.sum().backward()
-    for (gname, attr), leaf in leaves.items():
-        ref = gold['grad/gen|%s|%s' % (gname, attr)]
-        mine = leaf.grad.real.cpu().numpy().reshape(-1)
-        rel = np.abs(mine - ref) / (np.abs(ref).max() + 1e-300)
-        assert rel.max() < 1e-6, (gname, attr, mine, ref)
+    assert_gradients_match(gold, leaves, to_numpy=lambda t: t.cpu().numpy())
 
 
 def test_gradients_tiled_batch_and_shared_parameter():

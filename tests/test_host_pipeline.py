@@ -14,6 +14,9 @@ from tests import helpers
 CASES = [(g + '_' + s, g) for g in ('ibb', 'ibb_trans', 'ibb_wc', 'ieee9', 'k2a') for s in ('heun', 'euler', 'rk4')]
 CASES += [('k2a_batch_heun', 'k2a'), ('ieee9_persimz_heun', 'ieee9'), ('ieee9_two_events_heun', 'ieee9'),
           ('k2a_two_events_rk4', 'k2a'), ('ibb_param_event_heun', 'ibb'), ('k2a_param_event_rk4', 'k2a')]
+# reference outputs on the grids bench.py / BASELINE.json name (IEEE 39-bus incl. rows of the bench's own parameter draw,
+# the tiled grid of config 5 at 20 and at the full 100 generators)
+CASES += [('ieee39_heun', 'ieee39'), ('ieee39_batch_heun', 'ieee39'), ('tiled20_rk4', 'tiled20'), ('tiled100_rk4', 'tiled100')]
 
 
 @pytest.mark.parametrize('case,grid', CASES)

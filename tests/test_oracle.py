@@ -75,6 +75,12 @@ def test_oracle_matches_reference_golden_arrays(grid_name, ref_file):
     ('ieee9_persimz_heun', 'ieee9', 1e-9),
     ('ieee9_two_events_heun', 'ieee9', 1e-9),
     ('k2a_two_events_rk4', 'k2a', 1e-9),
+    # the configurations bench.py and BASELINE.json name (builder-authored grids in the reference's schema, run through
+    # the unmodified reference by oracle/gen_golden.py: headline_cases)
+    ('ieee39_heun', 'ieee39', 1e-9),                 # config 3 grid, nominal, full 2000 Heun steps
+    ('ieee39_batch_heun', 'ieee39', 1e-9),           # rows 0..3 of the bench's own U(0.5,2) parameter draw
+    ('tiled20_rk4', 'tiled20', 1e-9),                # config 5 family: 100 buses / 20 generators, RK4
+    ('tiled100_rk4', 'tiled100', 1e-9),              # config 5 grid itself: 500 buses / 100 generators, RK4
 ])
 def test_oracle_batches_and_events(case, grid_name, tol):
     gold, mine, out, inp = run_case(case, grid_name)

@@ -76,9 +76,17 @@ def test_two_rank_sharding_matches_single_process():
 
 def test_shard_ranges_cover_the_batch():
     from diffpssi_b200 import sharding
-    for P, world in ((65536, 8), (7, 3), (5, 8)):
+    for P, world in ((65536, 8), (7, 3), (8, 8)):
         cuts = [sharding.shard_range(P, world, r) for r in range(world)]
         assert cuts[0][0] == 0 and cuts[-1][1] == P
         assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
         sizes = [hi - lo for lo, hi in cuts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_fewer_trajectories_than_ranks_is_rejected_up_front():
+    """A rank with zero rows would raise before the first collective and leave the others hanging in it."""
+    import pytest
+    from diffpssi_b200 import sharding
+    with pytest.raises(ValueError, match='cannot be sharded'):
+        sharding.shard_range(5, 8, 0)
