@@ -197,7 +197,7 @@ int dps_plan_info(const dps_plan* plan, int32_t* block_threads, int32_t* sims_pe
 // a single launch).
 static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int step_end, const double* x_in,
                          const double* upar, const double* vpar, const double* zsub, double* rec, double* x_out,
-                         double* ckpt, void* stream, const char* who) {
+                         double* ckpt, void* workspace, size_t workspace_bytes, void* stream, const char* who) {
     if (!plan) { set_error("%s: null plan", who); return 1; }
     if (P < 1) { set_error("%s: P must be >= 1", who); return 1; }
     if (!x_in || !upar || !zsub) { set_error("%s: null input pointer", who); return 1; }
@@ -230,6 +230,13 @@ static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int st
             p.P = P; p.x0 = x_in; p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.rec = rec; p.ckpt = ckpt; p.x_final = x_out;
             p.step_begin = begin; p.step_end = end; p.n_seg = seg1 - seg0;
             for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[seg0 + i]; p.seg_cfg[i] = plan->seg_cfg[seg0 + i]; }
+            // optional work-queue scheduling (dps_internal.h): counter + one progress word per block group
+            if (workspace != nullptr && workspace_bytes >= 2 * sizeof(int) && ((uintptr_t)workspace % sizeof(int)) == 0) {
+                p.q_counter = (int*)workspace;
+                p.q_progress = (int*)workspace + 1;
+                const size_t cap = workspace_bytes / sizeof(int) - 1;
+                p.q_capacity = cap > 0x3fffffff ? 0x3fffffff : (int)cap;
+            }
             e = launch_forward(p, plan->g_template, plan->cmask, plan->pmode, st, nullptr);
         }
         if (e != cudaSuccess) { set_error("%s: launch failed: %s", who, cudaGetErrorString(e)); return 3; }
@@ -241,15 +248,24 @@ static int forward_range(const dps_plan* plan, int64_t P, int step_begin, int st
 }
 
 int dps_forward(const dps_plan* plan, int64_t P, const double* x0, const double* upar, const double* vpar,
-                const double* zsub, double* rec, double* x_final, double* ckpt, void* stream) {
+                const double* zsub, double* rec, double* x_final, double* ckpt, void* workspace, size_t workspace_bytes,
+                void* stream) {
     if (!plan) { set_error("dps_forward: null plan"); return 1; }
-    return forward_range(plan, P, 0, plan->topo.n_steps, x0, upar, vpar, zsub, rec, x_final, ckpt, stream, "dps_forward");
+    return forward_range(plan, P, 0, plan->topo.n_steps, x0, upar, vpar, zsub, rec, x_final, ckpt, workspace,
+                         workspace_bytes, stream, "dps_forward");
 }
 
 int dps_forward_range(const dps_plan* plan, int64_t P, int32_t step_begin, int32_t step_end, const double* x_in,
                       const double* upar, const double* vpar, const double* zsub, double* rec, double* x_out,
-                      double* ckpt, void* stream) {
-    return forward_range(plan, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt, stream, "dps_forward_range");
+                      double* ckpt, void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_range(plan, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt, workspace,
+                         workspace_bytes, stream, "dps_forward_range");
+}
+
+size_t dps_forward_workspace_bytes(const dps_plan* plan, int64_t P) {
+    if (!plan || P < 1 || plan->wide) return 0;
+    // one dequeue counter + one progress word per block group; a group holds at least 8 trajectories
+    return sizeof(int) * (size_t)(P / 8 + 66);
 }
 
 int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const double* z_im, const double* yd_re,

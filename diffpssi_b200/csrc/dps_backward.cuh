@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(BwdCfg<G>::THREADS, 2)
 dps_adjoint_kernel(const BwdParams p) {
     using Cfg = BwdCfg<G>;
     constexpr int SPW = Cfg::SPW;
-    constexpr int NS = DPS_N_STATES;
+    // live states per generator: a bare machine (no controllers anywhere) carries 6, its 7 controller rows are zero.  The
+    // per-step scratch, the register arrays and the sweep only hold NS of them; NSG is the stride of the 13-row buffers.
+    constexpr int NS = CTRL ? DPS_N_STATES : 6;
+    constexpr int NSG = DPS_N_STATES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* s_xch = reinterpret_cast<double2*>(smem_raw);                       // [WARPS][2][32] exchange lines
     double* s_upar = reinterpret_cast<double*>(s_xch + Cfg::WARPS * 64);         // [G][DPS_N_SLOTS]
@@ -175,7 +178,7 @@ dps_adjoint_kernel(const BwdParams p) {
     SlotGrads<NGP> gp;
 #pragma unroll
     for (int k = 0; k < NS; ++k)
-        lam[k] = (p.grad_xf != nullptr) ? p.grad_xf[((long long)g * NS + k) * P + s] : 0.0;
+        lam[k] = (p.grad_xf != nullptr) ? p.grad_xf[((long long)g * NSG + k) * P + s] : 0.0;
 #pragma unroll
     for (int k = 0; k < NGP; ++k) gp.v[k] = 0.0;
     gp.dummy = 0.0;
@@ -190,8 +193,8 @@ dps_adjoint_kernel(const BwdParams p) {
         const int k1 = (k0 + C < p.n_steps) ? (k0 + C) : p.n_steps;
         // ---- re-integrate the segment, keeping the state at the start of every step ----------------------------------
         {
-            double x[NS], xs[NS], acc[NS], f[NS];
-            const double* src = p.ckpt + (((long long)ck * p.n_gen + g) * NS) * P + s;
+            double x[NS], xs[NS], acc[NS], f[NSG];
+            const double* src = p.ckpt + (((long long)ck * p.n_gen + g) * NSG) * P + s;
 #pragma unroll
             for (int k = 0; k < NS; ++k) x[k] = src[(long long)k * P];
             for (int step = k0; step < k1; ++step) {
@@ -267,7 +270,7 @@ dps_adjoint_kernel(const BwdParams p) {
             // stage inputs and their voltages
 #pragma unroll
             for (int i = 0; i < n_stages; ++i) {
-                double f[NS];
+                double f[NSG];
                 Algebraics alg;
                 eval_stage(X[i], cfg, sds[i], cds[i], vres[i], vims[i], f, alg);
                 if (i + 1 < n_stages) {
@@ -288,12 +291,12 @@ dps_adjoint_kernel(const BwdParams p) {
 #pragma unroll
                 for (int k = 0; k < NS; ++k) { dk[k] = bi * lam[k] + cn * dxn[k]; dx[k] = 0.0; }
                 AlgCot ac = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (i == n_stages - 1 && live && (rec_mask >> NS)) {
+                if (i == n_stages - 1 && live && (rec_mask >> NSG)) {
                     const double* gr = p.grad_rec + (long long)step * P + sim;
                     double* av[7] = {&ac.p_e, &ac.i_d, &ac.i_q, &ac.v_re, &ac.v_im, &ac.e_fd, &ac.p_m};
 #pragma unroll
                     for (int k = 0; k < 7; ++k)
-                        if (rec_mask & (1u << (NS + k))) *av[k] = gr[ch[NS + k] * cs];
+                        if (rec_mask & (1u << (NSG + k))) *av[k] = gr[ch[NSG + k] * cs];
                 }
                 double dsd, dcd, dv_re, dv_im;
                 stage_vjp<CTRL>(X[i], par, ctrl, p.fn, sds[i], cds[i], vres[i], vims[i], dk, ac, dx, gp, dsd, dcd, dv_re, dv_im);
@@ -359,9 +362,10 @@ dps_adjoint_kernel(const BwdParams p) {
     }
 
     if (live) {
-        double* dst = p.g_x0 + (long long)g * NS * P + s;
+        double* dst = p.g_x0 + (long long)g * NSG * P + s;
 #pragma unroll
         for (int k = 0; k < NS; ++k) dst[(long long)k * P] = lam[k];
+        for (int k = NS; k < NSG; ++k) dst[(long long)k * P] = 0.0;
         const short* wr = p.want_row + g * DPS_N_SLOTS;
 #pragma unroll
         for (int k = 0; k < NGP; ++k)

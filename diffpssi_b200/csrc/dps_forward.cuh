@@ -60,7 +60,10 @@ struct FwdCfg {
 // RMASK: compile-time copy of the regular recorder's field mask (dps_internal.h), or -1 for "decide at run time".
 // The recorder of every benchmark configuration -- omega of each generator, mask 0x1 -- then is ONE predicated
 // streaming store per step instead of ~45 instructions of mask tests and channel arithmetic.
-template <int G, int CM, int PMODE, int ZPS, int SOLVER, int RMASK = -1>
+// QUEUED: compile-time switch of the work-queue prologue / epilogue (dps_internal.h).  A template parameter rather than a
+// run-time flag because the static launch then keeps its step bounds in the constant bank and compiles to exactly the
+// pre-queue code (the run-time flag cost it 3 % through a different register allocation).
+template <int G, int CM, int PMODE, int ZPS, int SOLVER, int RMASK = -1, bool QUEUED = false>
 __global__ void __launch_bounds__(FwdCfg<G>::THREADS, FwdCfg<G>::MIN_BLOCKS)
 dps_step_kernel(const FwdParams p) {
     using C = FwdCfg<G>;
@@ -90,9 +93,7 @@ dps_step_kernel(const FwdParams p) {
     const bool gen_live = (sl < SPW) && (gl < p.n_gen);     // template G may exceed the real generator count
     const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
-    const long long sim = ((long long)blockIdx.x * C::WARPS + warp) * SPW + sl;
-    const bool live = gen_live && (sim < P);
-    const long long s = (sim < P) ? sim : (P - 1);
+    __shared__ int s_item;                         // work queue: the item this block is processing
 
     for (int i = threadIdx.x; i < G * DPS_N_SLOTS; i += blockDim.x) {
         const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
@@ -116,6 +117,38 @@ dps_step_kernel(const FwdParams p) {
 
     const double* up = s_upar + g * UPS;
     const int ctrl = (CM >= 0) ? CM : p.ctrl[g];
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
+    constexpr bool queued = QUEUED;
+
+    // A block integrates ONE work item: block group `group` (WARPS * SPW trajectories) over steps [step_begin, step_end).
+    // Plain launch: group = blockIdx.x, all steps.  Queued launch (dps_internal.h): one block per (group, step chunk) item;
+    // the block takes a ticket from an atomic counter (tickets, not blockIdx, define the order: whoever holds ticket i
+    // runs, and every ticket below i was taken by a block that runs or has finished, so waiting for an earlier item cannot
+    // deadlock whatever order the hardware dispatches blocks in) and the state of a group travels between its chunks
+    // through x_final.
+    long long group = blockIdx.x;
+    int chunk = 0, n_chunks = 1;
+    if (queued) {
+        if (threadIdx.x == 0) s_item = atomicAdd(p.q_counter, 1);
+        __syncthreads();
+        // REDUX: tells the compiler that the ticket is warp-uniform, which keeps the step loop's bounds and the trigonometric
+        // / controller constants on the uniform datapath (a plain shared-memory load made the whole loop "possibly
+        // divergent": +10 % instructions, 20 % slower)
+        const int item = __reduce_max_sync(0xffffffffu, s_item);
+        chunk = item / p.q_groups;
+        group = item - chunk * p.q_groups;
+        n_chunks = p.q_items / p.q_groups;
+        // chunk c of a group starts from the state chunk c-1 left behind; that item holds an earlier ticket
+        if (chunk > 0 && threadIdx.x == 0)
+            while (dps_ld_acquire(p.q_progress + group) < chunk) __nanosleep(100);
+        __syncthreads();
+    }
+    const int step_begin = queued ? p.step_begin + chunk * p.q_chunk_steps : p.step_begin;
+    const int step_end = (queued && chunk + 1 < n_chunks) ? step_begin + p.q_chunk_steps : p.step_end;
+    const long long sim = ((long long)(queued ? group : (long long)blockIdx.x) * C::WARPS + warp) * SPW + sl;
+    const bool live = gen_live && (sim < P);
+    const long long s = (sim < P) ? sim : (P - 1);
 
     // ---- parameter access -------------------------------------------------------------------------------------------
     double pm[DPS_N_REG_SLOTS];
@@ -137,9 +170,11 @@ dps_step_kernel(const FwdParams p) {
 
     double x[NS];
     {
-        const double* src = p.x0 + (long long)g * DPS_N_STATES * P + s;   // state at step_begin
+        // state at step_begin: the caller's x0, or what the previous chunk of this group left in x_final (written by
+        // another SM: read through L2, never from a stale L1 line)
+        const double* src = ((!queued || chunk == 0) ? p.x0 : p.x_final) + (long long)g * DPS_N_STATES * P + s;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) x[k] = src[(long long)k * P];
+        for (int k = 0; k < NS; ++k) x[k] = (!queued || chunk == 0) ? src[(long long)k * P] : __ldcg(src + (long long)k * P);
     }
 
     // ---- network rows -------------------------------------------------------------------------------------------------
@@ -164,12 +199,11 @@ dps_step_kernel(const FwdParams p) {
 
     // configuration schedule: (first step, cfg) change points, ascending
     int seg = 0;
-    while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= p.step_begin) ++seg;
+    while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= step_begin) ++seg;
     int cfg = p.seg_cfg[seg];
     int next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
     load_z_row(cfg);
 
-    const double dt = p.dt, hdt = 0.5 * p.dt;
     const unsigned rec_mask = live ? p.rec_mask[g] : 0u;
     // regular recorder layout (dps_internal.h): launch-uniform field mask, channel = rec_fbase[field] + generator
     const bool rec_regular = (RMASK >= 0) ? true : (p.rec_regular != 0);
@@ -182,10 +216,9 @@ dps_step_kernel(const FwdParams p) {
         int q = 0;
 #pragma unroll
         for (int k = 0; k < DPS_N_STATES; ++k)
-            if ((RMASK >> k) & 1) rec_run[q++] = rec_thread + (long long)p.rec_fbase[k] * rec_cs + (long long)p.step_begin * P;
+            if ((RMASK >> k) & 1) rec_run[q++] = rec_thread + (long long)p.rec_fbase[k] * rec_cs + (long long)step_begin * P;
     }
-    const int n_extra_iter = (p.n_obs > p.n_gen) ? (p.n_obs - p.n_gen + p.n_gen - 1) / p.n_gen : 0;
-    int step = p.step_begin;
+    int step = step_begin;
     int buf = 0;
     // dummy lanes of a partially filled warp read the last real group
     double2* cur_w = s_cur + warp * 64;
@@ -293,7 +326,7 @@ dps_step_kernel(const FwdParams p) {
         }
     };
 
-    for (; step < p.step_end; ++step) {
+    for (; step < step_end; ++step) {
 #if DPS_REC_SYNC_STEPS > 0
         // The warps of a block are independent; without a bound on their drift the 24-byte pieces they write into the
         // same 32-byte DRAM sectors of a recorder row arrive further apart than L2 keeps a dirty line, and every piece
@@ -398,6 +431,16 @@ dps_step_kernel(const FwdParams p) {
         if (NS < DPS_N_STATES)
             for (int k = NS; k < DPS_N_STATES; ++k) dst[(long long)k * P] = 0.0;
     }
+    if (queued) {
+        // publish the chunk: every thread's state stores first (fence), then the group's progress counter
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // the ticket is re-read instead of kept: nothing of the queue stays live in registers across the step loop
+            const int item = s_item, c = item / p.q_groups;
+            dps_st_release(p.q_progress + (item - c * p.q_groups), c + 1);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -410,7 +453,7 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
     if constexpr (RMASK < 0 && ZPS == 0 && PMODE != 2 && CM >= 0) {
         if (p.rec_regular && p.rec_umask == 0x1u) return launch_one<G, CM, PMODE, ZPS, SOLVER, 0x1>(p, stream, regs);
     }
-    auto kern = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER, RMASK>;
+    auto kern = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER, RMASK, false>;
     if (regs) {
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, kern);
@@ -427,6 +470,22 @@ static cudaError_t launch_one(const FwdParams& p, cudaStream_t stream, int* regs
     }
     const long long sims_per_block = (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + sims_per_block - 1) / sims_per_block;
+    // the work-queue variant exists for the fast paths (batch-shared network, register / constant-bank constants)
+    if constexpr (ZPS == 0 && PMODE != 2) {
+        auto kern_q = dps_step_kernel<G, CM, PMODE, ZPS, SOLVER, RMASK, true>;
+        FwdParams q = p;
+        unsigned grid = (unsigned)blocks;
+        cudaError_t e = plan_work_queue(q, (const void*)kern_q, C::THREADS, smem, blocks, &grid, stream);
+        if (e != cudaSuccess) return e;
+        if (q.q_items > 0) {
+            if (smem > 48 * 1024) {
+                e = cudaFuncSetAttribute(kern_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            kern_q<<<grid, C::THREADS, smem, stream>>>(q);
+            return cudaGetLastError();
+        }
+    }
     kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }

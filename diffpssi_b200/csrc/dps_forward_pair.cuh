@@ -15,11 +15,14 @@
 //
 // Same equations (dps_model.cuh), same exchange scheme (warp-private shared-memory lines), same recorder layout and the
 // same periodic block barrier as dps_step_kernel; results are bit-identical to it (tests/test_cuda_parity.py).  254
-// registers, 8 warps per SM of 6 trajectories each: a "wave" is 7104 trajectories, so the dispatcher (try_pair_kernel,
-// called from launch_forward_g) only uses it from 16 384 trajectories per GPU on.  Measured (IEEE-39, Heun, T = 2000):
-//   trajectories   8192    16384   32768   49152   65536
-//   pair kernel    5.49    8.97    17.61   24.61   33.22  ms      FP64 pipe 77 % busy, 218 instructions per trajectory-stage
-//   dps_step_kernel 4.89   9.43    17.62   25.81   34.05  ms      FP64 pipe 73.5 %, 245 instructions
+// registers, 8 warps per SM of 6 trajectories each: a "wave" is 7104 trajectories.  Measured (IEEE-39, Heun, T = 2000;
+// "static" = one block per group for all steps, "queue" = (group, step chunk) work items, plan_work_queue below):
+//   trajectories            8192    16384   32768   65536
+//   pair kernel, static     5.49    8.97    17.61   33.21  ms     FP64 pipe 77 % busy, 218 instructions per trajectory-stage
+//   pair kernel, queue      4.28    8.58    16.73   32.78  ms
+//   dps_step_kernel, static 4.89    9.43    17.62   34.05  ms     FP64 pipe 73.5 %, 245 instructions
+//   dps_step_kernel, queue  4.38    8.75    17.39   34.26  ms
+// With the queue the pair kernel wins from the 8-GPU shard size (8192) on: that is the dispatcher's threshold.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -43,15 +46,57 @@ struct ParamPair {
     }
 };
 
+// Decide whether a launch of `groups` block groups runs as a work queue of (group, step chunk) items, one block each, (FwdParams::q_*, dps_internal.h) and set it up.  Worth it when the groups make only a few waves over the resident
+// block slots: the last, partly filled wave of a static launch then runs latency-bound for every step of the run
+// (8192 trajectories per GPU = 1.5 waves of dps_step_kernel: 4.89 ms against 4.15 ms for an eighth of 65 536).
+// Needs the caller's forward workspace (q_counter / q_progress, zeroed here on the stream) and x_final (state carrier).
+static cudaError_t plan_work_queue(FwdParams& q, const void* kern, int threads, size_t smem, long long groups, unsigned* grid,
+                                   cudaStream_t stream) {
+    q.q_items = 0;
+    if (q.q_counter == nullptr || q.x_final == nullptr || groups > q.q_capacity) return cudaSuccess;
+    const char* env = getenv("DPS_QUEUE_ROUNDS");              // experiments / tests: 0 = never queue
+    const int rounds = env ? atoi(env) : 12;                   // measured at 8192 trajectories: 6..24 rounds within 1.5 %
+    const int steps = q.step_end - q.step_begin;
+    if (rounds == 0 || steps < 64 || groups > 0x3fffffff) return cudaSuccess;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    const long long slots = (long long)sms * per_sm;
+    if (slots < 1 || groups <= slots) return cudaSuccess;     // one wave: everything is resident at once anyway
+    long long n_chunks = ((long long)rounds * slots + groups - 1) / groups;
+    if (n_chunks < 2) return cudaSuccess;                      // many waves: the tail is already a small fraction
+    int chunk_steps = (int)((steps + n_chunks - 1) / n_chunks);
+    chunk_steps = (chunk_steps + 15) & ~15;                    // keeps the recorder's 16-step block barrier aligned
+    if (chunk_steps < 32) chunk_steps = 32;
+    n_chunks = (steps + chunk_steps - 1) / chunk_steps;
+    if (n_chunks < 2 || groups * n_chunks > 0x3fffffff) return cudaSuccess;
+    q.q_items = (int)(groups * n_chunks);
+    q.q_groups = (int)groups;
+    q.q_chunk_steps = chunk_steps;
+    *grid = (unsigned)q.q_items;                              // one block per item; tickets give the order
+    return cudaMemsetAsync(q.q_counter, 0, sizeof(int) * (size_t)(groups + 1), stream);   // counter + progress[groups]
+}
+
 template <int G>
 struct PairCfg {
     static constexpr int SPW = 32 / G;             // trajectory PAIRS per warp
-    static constexpr int WARPS = 4;
+#ifndef DPS_PAIR_WARPS
+#define DPS_PAIR_WARPS 4
+#endif
+#ifndef DPS_PAIR_MIN_BLOCKS
+#define DPS_PAIR_MIN_BLOCKS 2
+#endif
+    static constexpr int WARPS = DPS_PAIR_WARPS;
     static constexpr int THREADS = 32 * WARPS;
+    static constexpr int MIN_BLOCKS = DPS_PAIR_MIN_BLOCKS;
 };
 
-template <int G, int SOLVER, int RMASK>
-__global__ void __launch_bounds__(PairCfg<G>::THREADS, 2)
+template <int G, int SOLVER, int RMASK, bool QUEUED = false>
+__global__ void __launch_bounds__(PairCfg<G>::THREADS, PairCfg<G>::MIN_BLOCKS)
 dps_step_pair_kernel(const FwdParams p) {
     using C = PairCfg<G>;
     constexpr int SPW = C::SPW, NS = DPS_N_STATES, CM = 7;
@@ -68,14 +113,7 @@ dps_step_pair_kernel(const FwdParams p) {
     const bool gen_live = (sl < SPW) && (gl < p.n_gen);
     const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
-    const long long sim0 = (((long long)blockIdx.x * C::WARPS + warp) * SPW + sl) * 2;   // this thread: sim0, sim0 + 1
-    bool live[2];
-    long long s[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        live[u] = gen_live && (sim0 + u < P);
-        s[u] = (sim0 + u < P) ? sim0 + u : (P - 1);
-    }
+    __shared__ int s_item;                         // work queue: the item this block is processing
 
     for (int i = threadIdx.x; i < C::WARPS * 128; i += blockDim.x) s_cur[i] = make_double2(0.0, 0.0);
     for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
@@ -86,6 +124,34 @@ dps_step_pair_kernel(const FwdParams p) {
         s_zi[i] = ok ? e[1] : 0.0;
     }
     __syncthreads();
+
+    const double dt = p.dt, hdt = 0.5 * p.dt;
+    constexpr bool queued = QUEUED;
+
+    // one work item per block (see dps_step_kernel): block group `group` over steps [step_begin, step_end)
+    long long group = blockIdx.x;
+    int chunk = 0, n_chunks = 1;
+    if (queued) {
+        if (threadIdx.x == 0) s_item = atomicAdd(p.q_counter, 1);
+        __syncthreads();
+        const int item = __reduce_max_sync(0xffffffffu, s_item);     // REDUX: provably warp-uniform ticket
+        chunk = item / p.q_groups;
+        group = item - chunk * p.q_groups;
+        n_chunks = p.q_items / p.q_groups;
+        if (chunk > 0 && threadIdx.x == 0)
+            while (dps_ld_acquire(p.q_progress + group) < chunk) __nanosleep(100);
+        __syncthreads();
+    }
+    const int step_begin = queued ? p.step_begin + chunk * p.q_chunk_steps : p.step_begin;
+    const int step_end = (queued && chunk + 1 < n_chunks) ? step_begin + p.q_chunk_steps : p.step_end;
+    const long long sim0 = (((long long)(queued ? group : (long long)blockIdx.x) * C::WARPS + warp) * SPW + sl) * 2;   // this thread: sim0, sim0 + 1
+    bool live[2];
+    long long s[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        live[u] = gen_live && (sim0 + u < P);
+        s[u] = (sim0 + u < P) ? sim0 + u : (P - 1);
+    }
 
     // ---- constants ----------------------------------------------------------------------------------------------------
     double sh[DPS_N_REG_SLOTS], pm[2][DPS_N_REG_SLOTS];
@@ -102,19 +168,18 @@ dps_step_pair_kernel(const FwdParams p) {
     double x[2][NS];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        const double* src = p.x0 + (long long)g * DPS_N_STATES * P + s[u];
+        const double* src = ((!queued || chunk == 0) ? p.x0 : p.x_final) + (long long)g * DPS_N_STATES * P + s[u];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) x[u][k] = src[(long long)k * P];
+        for (int k = 0; k < NS; ++k) x[u][k] = (!queued || chunk == 0) ? src[(long long)k * P] : __ldcg(src + (long long)k * P);
     }
 
     int seg = 0;
-    while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= p.step_begin) ++seg;
+    while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= step_begin) ++seg;
     int cfg = p.seg_cfg[seg];
     int next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
     const double* zcol_r = s_zr + cfg * G * G + gl;
     const double* zcol_i = s_zi + cfg * G * G + gl;
 
-    const double dt = p.dt, hdt = 0.5 * p.dt;
     // recorder: one running pointer per recorded field; the thread's two trajectories are adjacent in every row
     constexpr int N_RUN = __builtin_popcount((unsigned)RMASK & 0x1FFFu);
     const long long rec_cs = (long long)p.n_steps * P;
@@ -124,7 +189,7 @@ dps_step_pair_kernel(const FwdParams p) {
 #pragma unroll
         for (int k = 0; k < DPS_N_STATES; ++k)
             if ((RMASK >> k) & 1)
-                rec_run[q++] = p.rec + ((long long)g + p.rec_fbase[k]) * rec_cs + (long long)p.step_begin * P + sim0;
+                rec_run[q++] = p.rec + ((long long)g + p.rec_fbase[k]) * rec_cs + (long long)step_begin * P + sim0;
     }
     int buf = 0;
     double2* cur_w = s_cur + warp * 128;
@@ -173,7 +238,7 @@ dps_step_pair_kernel(const FwdParams p) {
         }
     };
 
-    for (int step = p.step_begin; step < p.step_end; ++step) {
+    for (int step = step_begin; step < step_end; ++step) {
 #if DPS_REC_SYNC_STEPS > 0
         if ((step & (DPS_REC_SYNC_STEPS - 1)) == 0) __syncthreads();      // see dps_step_kernel
 #endif
@@ -226,6 +291,15 @@ dps_step_pair_kernel(const FwdParams p) {
                 for (int k = 0; k < NS; ++k) dst[(long long)k * P] = x[u][k];
             }
     }
+    if (queued) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // the ticket is re-read instead of kept: nothing of the queue stays live in registers across the step loop
+            const int item = s_item, c = item / p.q_groups;
+            dps_st_release(p.q_progress + (item - c * p.q_groups), c + 1);
+        }
+    }
 }
 
 // Can this launch use the pair kernel?  (see the header comment)
@@ -243,7 +317,8 @@ static bool pair_kernel_applies(const FwdParams& p, int cmask, int pmode, long l
 template <int G, int SOLVER>
 static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, int* regs) {
     using C = PairCfg<G>;
-    auto kern = dps_step_pair_kernel<G, SOLVER, 0x1>;
+    auto kern = dps_step_pair_kernel<G, SOLVER, 0x1, false>;
+    auto kern_q = dps_step_pair_kernel<G, SOLVER, 0x1, true>;
     if (regs) {
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, kern);
@@ -258,7 +333,19 @@ static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, i
     }
     const long long sims_per_block = (long long)C::WARPS * C::SPW * 2;
     const long long blocks = (p.P + sims_per_block - 1) / sims_per_block;
-    kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    FwdParams q = p;
+    unsigned grid = (unsigned)blocks;
+    cudaError_t e = plan_work_queue(q, (const void*)kern_q, C::THREADS, smem, blocks, &grid, stream);
+    if (e != cudaSuccess) return e;
+    if (q.q_items > 0) {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kern_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern_q<<<grid, C::THREADS, smem, stream>>>(q);
+    } else {
+        kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -266,7 +353,7 @@ static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, i
 template <int G>
 bool try_pair_kernel(const FwdParams& p, int cmask, int pmode, cudaStream_t stream, int* regs, int* spb, cudaError_t* err) {
     const char* env = getenv("DPS_PAIR_MIN_SIMS");                  // experiments / tests: 0 = always, huge = never
-    const long long min_sims = env ? atoll(env) : 16384;
+    const long long min_sims = env ? atoll(env) : 8192;
     if (!pair_kernel_applies<G>(p, cmask, pmode, min_sims)) return false;
     if (spb) *spb = PairCfg<G>::WARPS * PairCfg<G>::SPW * 2;
     *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN>(p, stream, regs)

@@ -42,7 +42,28 @@ struct FwdParams {
     int rec_regular;
     unsigned rec_umask;
     short rec_fbase[DPS_N_FIELDS];
+    // Work queue (q_items > 0): the launch is a PERSISTENT grid whose blocks pull (block group, step chunk) items from an
+    // atomic counter in chunk-major order instead of one block integrating one group for all steps.  With only a few
+    // "waves" of blocks per SM a static launch leaves the SMs half empty for the whole last wave (8192 trajectories per GPU:
+    // 1.5 waves); cut into chunks the same work spreads evenly.  The state travels between chunks through x_final
+    // ([n_gen][13][P], the kernel's own state layout) and q_progress[group] counts the finished chunks of a group.
+    int q_items, q_groups, q_chunk_steps;
+    int q_capacity;          // block groups the caller's workspace has progress counters for
+    int* q_counter;          // one int, zeroed before the launch
+    int* q_progress;         // [q_groups], zeroed before the launch
 };
+
+// Acquire / release on the per-group progress counters of the work queue (gpu scope).
+#ifdef __CUDACC__
+__device__ __forceinline__ int dps_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dps_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+#endif
 
 // Parameter block of the wide stepper: same scalars, tables sized for MAX_GW generators (~11 KB, passed by value).
 struct WideParams {

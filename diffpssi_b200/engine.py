@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DPS_B200_LIB') or os.path.join(_HERE, 'libdps_b200.so')   # override: kernel A/B experiments
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 N_STATES = 13
 N_SLOTS = 42
 N_FIELDS = 20
@@ -22,9 +22,10 @@ MAX_EXTRA_OBS = 64
 MAX_CFG = 16
 MAX_FAULT = 8
 
-EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes',
+EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes', 'dps_forward_workspace_bytes',
            'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_fp64_dmma_probe', 'dps_math_probe', 'dps_plan_info',
-           'dps_last_error', 'dps_abi_version')
+           'dps_last_error', 'dps_abi_version', 'dps_ident_loss_workspace_bytes', 'dps_ident_loss', 'dps_bfgs_step',
+           'dps_ident_control')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
 CH_GEN, CH_BUS_VRE, CH_BUS_VIM = 0, 1, 2
@@ -79,11 +80,19 @@ def load_library(path=None):
     lib.dps_workspace_bytes.restype = ctypes.c_size_t
     lib.dps_network_reduce.argtypes = [i64, i32, vp, vp, vp, vp, i32, ctypes.POINTER(i32), i32, ctypes.POINTER(i32),
                                        i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dbl, vp, vp]
-    lib.dps_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.dps_forward_range.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dps_forward_workspace_bytes.argtypes = [vp, i64]
+    lib.dps_forward_workspace_bytes.restype = ctypes.c_size_t
+    lib.dps_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.dps_forward_range.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.dps_backward.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint8), vp, vp, vp, vp,
                                  ctypes.c_size_t, vp]
     lib.dps_math_probe.argtypes = [i64, vp, vp, vp, vp]
+    lib.dps_ident_loss_workspace_bytes.argtypes = [i64, i32]
+    lib.dps_ident_loss_workspace_bytes.restype = ctypes.c_size_t
+    lib.dps_ident_loss.argtypes = [i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.dps_bfgs_step.argtypes = [i64, i32, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(vp), ctypes.POINTER(i32),
+                                  vp, vp, vp, vp, i32, i32, vp]
+    lib.dps_ident_control.argtypes = [vp, dbl, vp]
     lib.dps_fp64_peak_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     lib.dps_fp64_dmma_probe.argtypes = [i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     lib.dps_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
@@ -173,18 +182,32 @@ class Plan(object):
         return {'block_threads': a.value, 'sims_per_block': b.value, 'regs_per_thread': c.value,
                 'g_template': d.value}
 
+    def _forward_workspace(self, P, ref):
+        """(pointer, bytes) of the optional forward scratch (work-queue counters), one cached buffer per device."""
+        need = int(self.lib.dps_forward_workspace_bytes(self.handle, P))
+        if need == 0:
+            return None, 0
+        ws = self.__dict__.setdefault('_fwd_ws', {}).get(ref.device)
+        if ws is None or ws.numel() * 4 < need:
+            ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=ref.device)
+            self._fwd_ws[ref.device] = ws
+        return ctypes.c_void_p(ws.data_ptr()), ws.numel() * 4
+
     def forward(self, P, x0, upar, vpar, zsub, rec, x_final=None, ckpt=None):
         require_cuda()
         with _on_device_of(x0):
+            ws, ws_bytes = self._forward_workspace(P, x0)
             _check(self.lib, self.lib.dps_forward(self.handle, P, _ptr(x0), _ptr(upar), _ptr(vpar), _ptr(zsub),
-                                                  _ptr(rec), _ptr(x_final), _ptr(ckpt), _stream(x0)), 'dps_forward')
+                                                  _ptr(rec), _ptr(x_final), _ptr(ckpt), ws, ws_bytes, _stream(x0)),
+                   'dps_forward')
 
     def forward_range(self, P, step_begin, step_end, x_in, upar, vpar, zsub, rec, x_out, ckpt=None):
         require_cuda()
         with _on_device_of(x_in):
+            ws, ws_bytes = self._forward_workspace(P, x_in)
             _check(self.lib, self.lib.dps_forward_range(self.handle, P, step_begin, step_end, _ptr(x_in), _ptr(upar),
                                                         _ptr(vpar), _ptr(zsub), _ptr(rec), _ptr(x_out), _ptr(ckpt),
-                                                        _stream(x_in)), 'dps_forward_range')
+                                                        ws, ws_bytes, _stream(x_in)), 'dps_forward_range')
 
 
 def network_reduce(z_re, z_im, yd_re, yd_im, obs_bus, gen_bus, cfg_sets, y_fault, zsub):
@@ -233,3 +256,60 @@ def fp64_dmma_probe(iters=4096):
     tf, ms = ctypes.c_double(), ctypes.c_double()
     _check(lib, lib.dps_fp64_dmma_probe(iters, ctypes.byref(tf), ctypes.byref(ms)), 'dps_fp64_dmma_probe')
     return tf.value, ms.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# identification step on the device (csrc/dps_optim.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+def ident_loss(rec, target, vmin, vrange, state=None, want_grad=True, workspace=None):
+    """Default loss of the reference's optimisation loop (ps_optimization.py:87-101, 178-199) on ``rec`` [C,T,P] against
+    ``target`` [C,T,Pt] (Pt in {1, P}) -> (loss [P], g_rec [C,T,P] or None).  ``state``: [4] float64 device tensor that
+    receives the batch minimum and its row (see include/dps.h)."""
+    require_cuda()
+    lib = load_library()
+    C, T, P = rec.shape
+    Pt = target.shape[2]
+    loss = torch.empty(P, dtype=torch.float64, device=rec.device)
+    g = torch.empty_like(rec) if want_grad else None
+    need = int(lib.dps_ident_loss_workspace_bytes(P, T))
+    if workspace is None or workspace.numel() * 8 < need:
+        workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=rec.device)
+    with _on_device_of(rec):
+        _check(lib, lib.dps_ident_loss(P, T, C, Pt, _ptr(rec), _ptr(target), _ptr(vmin), _ptr(vrange), _ptr(loss), _ptr(g),
+                                       _ptr(state), ctypes.c_void_p(workspace.data_ptr()), workspace.numel() * 8,
+                                       _stream(rec)), 'dps_ident_loss')
+    return loss, g, workspace
+
+
+def _real_view(t):
+    """(device pointer, element stride in doubles) of the real part of a [P,1] / [P] float64 or complex128 tensor."""
+    if not t.is_cuda:
+        raise EngineError('optimiser state must live on a CUDA device; there is no CPU fallback')
+    if t.dtype == torch.complex128:
+        r = torch.view_as_real(t)                     # [..., 2]
+        return r.data_ptr(), 2 * (t.stride(0) if t.dim() else 1)
+    if t.dtype != torch.float64:
+        raise EngineError('optimisable parameters must be float64 or complex128')
+    return t.data_ptr(), (t.stride(0) if t.dim() else 1)
+
+
+def bfgs_step(params, grads, hesse, last_grad, last_sk, state, first_step, have_last):
+    """CustomBFGSREALOptimizer.step() (optimizers.py:52-111) on the device; ``params`` are updated in place."""
+    require_cuda()
+    lib = load_library()
+    n = len(params)
+    P = params[0].shape[0]
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    xp, xs = zip(*[_real_view(p.data) for p in params])
+    gp, gs = zip(*[_real_view(g) for g in grads])
+    with _on_device_of(hesse):
+        _check(lib, lib.dps_bfgs_step(P, n, (vp * n)(*xp), (i32 * n)(*xs), (vp * n)(*gp), (i32 * n)(*gs), _ptr(hesse),
+                                      _ptr(last_grad), _ptr(last_sk), _ptr(state), int(first_step), int(have_last),
+                                      _stream(hesse)), 'dps_bfgs_step')
+
+
+def ident_control(state, decay):
+    require_cuda()
+    lib = load_library()
+    with _on_device_of(state):
+        _check(lib, lib.dps_ident_control(_ptr(state), float(decay), _stream(state)), 'dps_ident_control')

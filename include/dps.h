@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DPS_ABI_VERSION 2
+#define DPS_ABI_VERSION 3
 
 /* ---- per-generator state layout (canonical: absent controllers keep zero slots) ----------------------------
  * reference order: machine(6) | exciter(lead-lag, PT1) | governor(PT1, lead-lag) | PSS(washout, LL1, LL2)
@@ -119,8 +119,15 @@ int dps_plan_destroy(dps_plan* plan);
 /* Number of checkpoints a forward call writes for this plan (0 if ckpt_stride == 0). */
 int64_t dps_n_checkpoints(const dps_plan* plan);
 
-/* Bytes of scratch dps_backward needs for P trajectories (dps_forward needs none). */
+/* Bytes of scratch dps_backward needs for P trajectories. */
 size_t dps_workspace_bytes(const dps_plan* plan, int64_t P);
+
+/* Bytes of the OPTIONAL scratch of dps_forward / dps_forward_range for P trajectories (a few bytes per trajectory;
+ * 0 when the plan's stepper has no use for it).  With it -- and with x_final / x_out non-NULL -- a launch whose blocks
+ * would make only a few "waves" over the SMs runs as a persistent grid that pulls (block of trajectories, chunk of
+ * steps) work items from a queue, so that a partly filled last wave does not idle most of the GPU for the whole run
+ * (e.g. the 8192-trajectory shards of the 8-GPU configuration).  Results are bit-identical with and without. */
+size_t dps_forward_workspace_bytes(const dps_plan* plan, int64_t P);
 
 /*
  * Fault re-reduction on the device.  Replaces the per-step
@@ -157,12 +164,15 @@ int dps_network_reduce(int64_t Bz, int32_t n_bus,
  *   zsub     [n_cfg][z_rows][z_cols][2][Bz] reduced impedance, Bz = z_per_sim ? P : 1
  *   rec      out [n_rec][n_steps][P]        == the reference's [batch, timestep, value] result viewed as
  *                                           rec.permute(2,1,0) (same memory order as simulator.py:546)
- *   x_final  out [n_gen][DPS_N_STATES][P]   states after the last step (may be NULL)
+ *   x_final  out [n_gen][DPS_N_STATES][P]   states after the last step (may be NULL); with a workspace it also carries
+ *                                           the state between the step chunks of the work queue
  *   ckpt     out [n_ckpt][n_gen][DPS_N_STATES][P] state *before* step k*ckpt_stride (NULL if ckpt_stride == 0)
  */
 int dps_forward(const dps_plan* plan, int64_t P,
                 const double* x0, const double* upar, const double* vpar, const double* zsub,
-                double* rec, double* x_final, double* ckpt, void* stream);
+                double* rec, double* x_final, double* ckpt,
+                void* workspace, size_t workspace_bytes,   /* dps_forward_workspace_bytes(); NULL / 0 = static launch */
+                void* stream);
 
 /*
  * Same as dps_forward for the step range [step_begin, step_end) only, starting from the state `x_in` (the state before
@@ -173,13 +183,14 @@ int dps_forward(const dps_plan* plan, int64_t P,
  */
 int dps_forward_range(const dps_plan* plan, int64_t P, int32_t step_begin, int32_t step_end,
                       const double* x_in, const double* upar, const double* vpar, const double* zsub,
-                      double* rec, double* x_out, double* ckpt, void* stream);
+                      double* rec, double* x_out, double* ckpt,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Discrete adjoint of dps_forward (what torch autograd does for the reference in
  * optimization_lib/ps_optimization.py:212).  Recomputes each checkpoint segment forward, then sweeps it
  * backwards.  Gradients are with respect to the kernel inputs; the host chains them into the torch graph of
- * the prologue.  Z is treated as constant (parameters that enter Y_dyn are not differentiable yet).
+ * the prologue, including -- on request -- dL/dZsub for parameters that enter Y_dyn (g_zsub below).
  *
  *   ckpt          [n_ckpt][n_gen][DPS_N_STATES][P]  checkpoints written by dps_forward (ckpt_stride > 0)
  *   grad_rec      [n_rec][n_steps][P]   dL/d rec
@@ -198,6 +209,43 @@ int dps_backward(const dps_plan* plan, int64_t P,
                  const double* grad_rec, const double* grad_x_final,
                  const uint8_t* want, double* g_x0, double* gslot, double* g_zsub,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the identification step on the device (reference: optimization_lib/) ------------------------
+ *
+ * dps_ident_loss: the reference's default loss with its min/max normalisation and the gradient autograd would return for
+ * ``loss.sum().backward()`` (ps_optimization.py:87-101, 178-199, 202, 212):
+ *     loss[p] = mean_t sum_c | (target - vmin)/vrange - (rec - vmin)/vrange |          (vmin/vrange NULL: no normalisation)
+ *   rec      [C][T][P]   recorder output of dps_forward
+ *   target   [C][T][Pt]  Pt = 1 (one target trajectory for the whole batch) or P
+ *   vmin, vrange [C][Pt] or both NULL
+ *   loss     out [P]
+ *   g_rec    out [C][T][P] d(sum_p loss[p])/d rec, or NULL
+ *   state    in/out [4] doubles {max_step, last_min_loss, cur_min_loss, cur_min_row} or NULL: cur_min_* receive the minimum
+ *            of nan_to_num(loss, 1e5) over the batch and its row (ps_optimization.py:202)
+ *   workspace  dps_ident_loss_workspace_bytes(P, T) bytes
+ */
+size_t dps_ident_loss_workspace_bytes(int64_t P, int32_t T);
+int dps_ident_loss(int64_t P, int32_t T, int32_t C, int64_t Pt, const double* rec, const double* target,
+                   const double* vmin, const double* vrange, double* loss, double* g_rec, double* state,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* dps_bfgs_step: CustomBFGSREALOptimizer.step() (optimizers.py:52-111) for every trajectory at once: BFGS on the inverse
+ * Hessian without line search; the first step is scaled to the maximum relative step, every step is clipped to it.
+ *   n            optimised parameters per trajectory (1..8)
+ *   x, grad      HOST arrays of n device pointers: real part of parameter i / of its gradient for trajectory p at
+ *                x[i][p * x_stride[i]] (stride 2 for complex128 [P,1] tensors, 1 for float64); x is updated in place
+ *                (``p.data += sk``, :83-85)
+ *   hesse        in/out [n][n][P]   last_grad, last_sk  in/out [n][P]
+ *   state        [4] doubles as above; state[0] (the current maximum relative step) is read
+ *   first_step   1: initialise hesse as :64-70.   have_last 0: no update of hesse yet (:89-92)
+ */
+int dps_bfgs_step(int64_t P, int32_t n, double* const* x, const int32_t* x_stride, const double* const* grad,
+                  const int32_t* grad_stride, double* hesse, double* last_grad, double* last_sk, const double* state,
+                  int32_t first_step, int32_t have_last, void* stream);
+
+/* dps_ident_control: ps_optimization.py:246-249 on the device state:
+ *     if last_min_loss and last_min_loss < cur_min_loss: max_step *= decay;   last_min_loss = cur_min_loss */
+int dps_ident_control(double* state, double decay, void* stream);
 
 /* Measurement helper: runs a dependent-chain-free DFMA loop on every SM and returns the achieved fp64
  * TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises.  Used by bench.py as the fp64 roofline denominator

@@ -52,7 +52,8 @@ def test_plan_validation_errors_are_reported():
     ck = engine.Plan(dict(topo, ckpt_stride=3))
     assert ck.n_checkpoints() == 2
     # null pointers are rejected before anything is launched
-    rc = lib.dps_forward(plan.handle, 8, None, None, None, None, None, None, None, None)
+    rc = lib.dps_forward(plan.handle, 8, None, None, None, None, None, None, None, None, 0, None)
+    assert lib.dps_forward_workspace_bytes(plan.handle, 8192) >= 4 * (8192 // 8 + 2)
     assert rc != 0 and b'null' in lib.dps_last_error()
 
 
@@ -65,3 +66,29 @@ def test_no_cpu_fallback():
     sim, _, _ = helpers.sim_from_gold('ibb_heun', 'ibb', device='cpu')
     with pytest.raises(engine.EngineError, match='no CPU fallback'):
         sim.run()
+
+
+def test_integration_doc_struct_matches_the_binding():
+    """INTEGRATION.md shows the ctypes struct a reference maintainer would write; a stale copy (a missing trailing member)
+    makes dps_plan_create read past the caller's struct.  Compare it field by field with engine.Topology and with the
+    member order of include/dps.h."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = doc[doc.index('class dps_topology(ctypes.Structure)'):doc.index('DPS_ABI_VERSION = ')]
+    doc_fields = []
+    for name, ptr_to, plain in re.findall(r"\('(\w+)',\s*ctypes\.(?:POINTER\((?:ctypes\.)?(\w+)\)|(\w+))\)", block):
+        doc_fields.append((name, 'ptr:' + ptr_to if ptr_to else plain))
+    mine = []
+    for name, ctype in engine.Topology._fields_:
+        tname = ctype.__name__
+        mine.append((name, 'ptr:' + tname[3:] if tname.startswith('LP_') else tname))
+    def norm(t):             # ctypes.c_int32 is an alias of c_int on this ABI; compare the resolved type names
+        pre, name = ('ptr:', t[4:]) if t.startswith('ptr:') else ('', t)
+        name = {'dps_channel': 'Channel'}.get(name, name)
+        return pre + (getattr(ctypes, name).__name__ if hasattr(ctypes, name) else name)
+    assert [(n, norm(t)) for n, t in doc_fields] == [(n, norm(t)) for n, t in mine]
+    # member order of the C header
+    hdr = open(os.path.join(ROOT, 'include', 'dps.h')).read()
+    body = hdr[hdr.index('typedef struct {\n    int32_t abi_version'):hdr.index('} dps_topology;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    assert re.findall(r'(\w+)\s*;', body) == [n for n, _ in mine]
+    assert 'DPS_ABI_VERSION = %d' % engine.ABI_VERSION in doc

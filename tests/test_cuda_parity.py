@@ -456,3 +456,29 @@ def test_host_prologue_equals_device_prologue():
         assert res.is_cuda
         out[pdev] = res.cpu().numpy()
     assert np.abs(out['cpu'] - out[None]).max() < 1e-12
+
+
+@pytest.mark.parametrize('pair_min', ['0', '999999999'])
+def test_work_queue_matches_static_launch(monkeypatch, pair_min):
+    """The (block group, step chunk) work queue (csrc/dps_internal.h: q_*) only reschedules the same arithmetic: a batch that
+    makes ~2.4 waves of blocks must come out bit-identical with the queue on (default) and off, for both stepping kernels,
+    with a fault inside one chunk and a chunk boundary inside the fault."""
+    from diffpssi_b200 import grids
+    rng = np.random.RandomState(31)
+    P = 148 * 3 * 12 * 2 + 517                    # > 2 waves of dps_step_kernel blocks, ragged
+    ov = {}
+    for g, (h, xdt) in grids.GENERATOR_NOMINALS['ieee39'].items():
+        ov[(g, 'h')] = h * rng.uniform(0.6, 1.8, P)
+        ov[(g, 'd')] = rng.uniform(0.0, 2.0, P)
+        ov[(g, 'x_d_t')] = xdt * rng.uniform(0.6, 1.8, P)
+    monkeypatch.setenv('DPS_PAIR_MIN_SIMS', pair_min)
+    out = {}
+    for rounds in ('0', '12', '40'):
+        monkeypatch.setenv('DPS_QUEUE_ROUNDS', rounds)
+        sim = _ieee39_sim(P, ov, T=500)
+        sim.sc_events = []
+        sim.add_sc_event(0.9, 1.3, 'B16')
+        _, res = sim.run()
+        out[rounds] = res.clone()
+        assert bool(torch.isfinite(res).all())
+    assert torch.equal(out['0'], out['12']) and torch.equal(out['0'], out['40'])
