@@ -178,6 +178,18 @@ class Shunt(_Component):
 # --------------------------------------------------------------------------------------------------
 # controller blocks   (reference: blocks.py:103-436)  -- one state each, float64 parameters
 # --------------------------------------------------------------------------------------------------
+class PIController(_Component):
+    """Proportional-integral block, ``output = k_p * input + k_i * state`` (reference blocks.py:7-100).  The reference
+    defines it for inverter controls but ships no model that uses it; it is a parameter container here like the other
+    blocks, so that a user-defined model can carry it."""
+    PARALLEL = ('k_p', 'k_i', 'state_1')
+
+    def __init__(self, k_p, k_i):
+        self.k_p, self.k_i = k_p, k_i
+        self.input = 0
+        self.state_1 = 0
+
+
 class PT1Limited(_Component):
     PARALLEL = ('t_pt1', 'gain_pt1', 'lim_min', 'lim_max')
 

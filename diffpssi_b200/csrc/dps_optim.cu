@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) dps_ident_loss_kernel(const Loss
             // (target - min)/range - (result - min)/range, as ps_optimization.py:194-195 then :99
             const double d = q.normalize ? ((yv - lo) / rg - (rv - lo) / rg) : (yv - rv);
             acc += fabs(d);
-            // d|d|/d result = -sign(d) / range; mean over time: 1/T.  sign(0) = 0 and NaN propagates, as in torch.
-            if (g) g[(long long)t * q.P] = ((d > 0.0) ? -1.0 : ((d < 0.0) ? 1.0 : d)) * inv_T / rg;
+            // d|d|/d result = -sign(d) / range; mean over time: 1/T.  torch: sign(0) = 0 and sign(NaN) = 0 as well (abs'
+            // backward multiplies by sgn(), which is (0 < x) - (x < 0)), so a NaN residual contributes no gradient here
+            if (g) g[(long long)t * q.P] = ((d > 0.0) ? -1.0 : ((d < 0.0) ? 1.0 : 0.0)) * inv_T / rg;
         }
     }
     q.partial[(long long)blockIdx.y * q.P + p] = acc;

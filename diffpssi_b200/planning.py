@@ -92,20 +92,33 @@ def pack_slots(init, P, device, memo=None):
     return upar, vpar, slot_vary
 
 
-def common_controller_constants(init, upar, slot_vary):
+def common_controller_constants(init, upar, slot_vary, memo=None):
     """Host list [N_SLOTS] of the controller constants when every generator has all three controllers and their
     (batch-uniform) constants are identical between generators -- the stepper then takes them as constant-bank operands
-    (``dps_topology.common_ctrl``).  None otherwise.  One small device->host read per run()."""
+    (``dps_topology.common_ctrl``).  None otherwise.
+
+    The values are baked into the plan, so a controller constant that requires grad (it changes from one optimisation step
+    to the next) rules the specialisation out.  ``memo`` (a dict living on the simulation) keeps the answer for as long as
+    the controller-constant tensors are the same objects at the same version: no device->host read per run(), which also
+    keeps run() capturable into a CUDA graph."""
     if any(f != (CTRL_AVR | CTRL_GOV | CTRL_PSS) for f in init.ctrl):
         return None
     G = len(init.ctrl)
     if any(slot_vary[g * N_SLOTS + k] >= 0 for g in range(G) for k in range(N_REG_SLOTS, N_SLOTS)):
         return None
+    tensors = [sl[name] for sl in init.slots for name in SLOTS[N_REG_SLOTS:]]
+    if any(t.requires_grad for t in tensors):
+        return None
+    key = tuple((id(t), t._version) for t in tensors)
+    hit = memo.get('common_ctrl') if memo is not None else None
+    if hit is not None and hit[0] == key:
+        return hit[2]
     host = upar.detach().cpu()
     tail = host[:, N_REG_SLOTS:]
-    if not bool((tail == tail[:1]).all()):
-        return None
-    return [float(v) for v in host[0]]
+    out = [float(v) for v in host[0]] if bool((tail == tail[:1]).all()) else None
+    if memo is not None:
+        memo['common_ctrl'] = (key, tensors, out)        # `tensors` keeps the keyed objects alive
+    return out
 
 
 def observed_rows(init, channel_keys):

@@ -170,7 +170,15 @@ class PowerSystemSimulation(object):
         self.get_generator_by_name(pss_model.gen).add_pss(self._par(pss_model))
 
     def add_inverter(self, inverter_model):
-        raise NotImplementedError('inverter models are outside the accelerated path (unused by the reference examples)')
+        """simulator.py:247-252: the model is attached to its bus like any other.  The reference ships no inverter model
+        (only the PIController block such a model would use, blocks.py:7-100), so there are no equations the stepping
+        kernels could integrate: ``run()`` refuses a bus model it does not know instead of silently ignoring it."""
+        bus = self._bus_of(inverter_model)
+        try:
+            inverter_model.enable_parallel_simulation(self.parallel_sims, self.prologue_device)
+        except TypeError:
+            inverter_model.enable_parallel_simulation(self.parallel_sims)       # reference signature
+        bus.add_model(inverter_model)
 
     def add_sc_event(self, start_time, end_time, bus):
         self.sc_events.append(ScEvent(start_time, end_time, self.bus_idxs[bus]))
@@ -193,8 +201,9 @@ class PowerSystemSimulation(object):
         (``p.data += ...``, as the reference's own optimiser does, optimization_lib/optimizers.py:83) bumps neither, so
         after such a write on a tensor that does NOT require grad call this before the next run().  (Tensors that require
         grad always bypass the caches.)"""
-        for k in ('_prologue_cache', '_pack_cache', '_schedule_cache'):
+        for k in ('_prologue_cache', '_schedule_cache'):
             self.__dict__.pop(k, None)
+        self.__dict__.setdefault('_pack_cache', {}).clear()
         self._uniform_cache = {}
 
     def reset(self):
@@ -215,6 +224,12 @@ class PowerSystemSimulation(object):
     # ------------------------------------------------------------------------------------------------------------
     def initialize(self):
         """Load flow, model initialisation, Z = inv(Y_dyn), initial bus voltages (simulator.py:438-450)."""
+        for bus in self.busses:
+            for m in bus.models:
+                if not isinstance(m, (SynchMachine, Load, Shunt)):
+                    raise NotImplementedError("bus model %r on %s has no kernel implementation: backend='cuda' integrates "
+                                              'SynchMachine (+ SEXS / TGOV1 / STAB1), constant-impedance loads and shunts'
+                                              % (type(m).__name__, bus.name))
         init = prologue.initialize(self, self.prologue_device)
         self.inverse_dynamic_y_matrix = init.Z0
         P = self.parallel_sims
@@ -257,7 +272,7 @@ class PowerSystemSimulation(object):
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
-        topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary)
+        topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary, self._pack_cache)
         topo['want_z'] = bool(net_grad)
         plan = engine.Plan(topo)
         self.last_plan = plan

@@ -402,6 +402,106 @@ def ident_range_grad_case(sel):
     save_case(name, t, rec, names, snap, events, 'heun', extra, stride=20)
 
 
+def _stub_matplotlib():
+    """optimization_lib/ps_optimization.py:7 imports matplotlib, which this image does not have; its plotting is only
+    reached with enable_plots=True / at the end of run().  A do-nothing stand-in lets the unmodified module import."""
+    import types
+    if 'matplotlib' in sys.modules:
+        return
+    mpl = types.ModuleType('matplotlib')
+    plt = types.ModuleType('matplotlib.pyplot')
+
+    class _Anything(object):
+        def __getattr__(self, name):
+            return _Anything()
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+        def __iter__(self):
+            return iter(())
+
+    def _plt_attr(name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return lambda *a, **k: _Anything()
+    plt.__getattr__ = _plt_attr
+    mpl.pyplot = plt
+    sys.modules['matplotlib'] = mpl
+    sys.modules['matplotlib.pyplot'] = plt
+
+
+def optimizer_cases(sel):
+    """Known answers for the optimiser step and the whole identification loop, from the reference's own classes:
+    CustomBFGSREALOptimizer (optimization_lib/optimizers.py:7-111) driven with seeded gradients, and
+    PowerSystemOptimization.run() (optimization_lib/ps_optimization.py:150-256) on the IBB model."""
+    import torch
+    rh._import_reference('torch')
+    _stub_matplotlib()
+    from src.diffpssi.optimization_lib.optimizers import CustomBFGSREALOptimizer
+    name = 'bfgs_reference'
+    if not sel or any(s in name for s in sel):
+        rng = np.random.RandomState(11)
+        for n, tag in ((3, ''), (5, '_n5'), (1, '_n1')):
+            P, K = 6, 7
+            x0 = rng.uniform(0.5, 3.0, (n, P))
+            grads = rng.normal(0, 1, (K, n, P)) * rng.uniform(0.01, 10.0, (1, n, 1))
+            params = [torch.tensor(x0[i].reshape(P, 1), dtype=torch.complex128, requires_grad=True) for i in range(n)]
+            opt = CustomBFGSREALOptimizer(params, max_step=0.1, decay=0.75, verbose=False)
+            traj, steps = [], []
+            for k in range(K):
+                for i, p_ in enumerate(params):
+                    p_.grad = torch.complex(torch.tensor(grads[k, i].reshape(P, 1)), torch.full((P, 1), 0.123 * (k + 1), dtype=torch.float64))
+                opt.step()
+                if k in (2, 4):
+                    opt.decrease_step_size()
+                traj.append(np.stack([p_.data.real.numpy().reshape(-1).copy() for p_ in params]))
+                steps.append(opt.max_step)
+            np.savez_compressed(os.path.join(GOLD, name + tag + '.npz'), x0=x0, grads=grads, traj=np.stack(traj),
+                                max_step_after=np.array(steps), decay=0.75, max_step=0.1, decrease_after=np.array([2, 4]),
+                                hesse=opt.hesse.numpy())
+            print('wrote', name + tag)
+    name = 'opt_ibb_reference'
+    if not sel or any(s in name for s in sel):
+        from src.diffpssi.optimization_lib.ps_optimization import PowerSystemOptimization
+        rng = np.random.RandomState(21)
+        P, K = 6, 4
+        grid = rh.load_example_grid(*GRIDS['ibb'])
+        ov = {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.6, 1.6, P),
+              ('gen', 'Gen 1', 'x_d_t'): 0.3 * rng.uniform(0.6, 1.6, P),
+              ('gen', 'Gen 1', 'd'): rng.uniform(0.3, 2.0, P)}
+        sim, leaves = rh.build(grid, P, 'heun', DT, 3.0, [(1, 1.05, 'Bus 1')], ov, requires_grad=True)
+        sim.set_record_function(lambda s_: [s_.busses[1].models[0].omega.real, s_.busses[1].models[0].e_q_st.real,
+                                            s_.busses[1].models[0].e_d_st.real])
+        target = torch.tensor(np.load(os.path.join(rh.REFERENCE_ROOT, 'tests', 'integration', 'data', 'ibb_model.npy'))[:600])
+        target = target * torch.ones((P,) + tuple(target.shape))
+        keys = list(leaves.keys())
+        params = [leaves[k] for k in keys]
+        opt = PowerSystemOptimization(sim, target, params_optimizable=params, param_names=['|'.join(k) for k in keys],
+                                      decay=0.75, max_step=0.1)
+        traj, losses = [], []
+        orig_step = opt.optimizer.step
+
+        def spy(**kw):
+            orig_step(**kw)
+            traj.append(np.stack([p_.data.real.numpy().reshape(-1).copy() for p_ in params]))
+        opt.optimizer.step = spy
+        orig_loss = opt.loss_function
+
+        def loss_spy(a, b):
+            out = orig_loss(a, b)
+            losses.append(out.detach().numpy().copy())
+            return out
+        opt.loss_function = loss_spy
+        os.environ.pop('DIFFPSSI_FORCE_OPT_ITERS', None)
+        opt.run(max_steps=K)
+        extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), keys=np.array(['|'.join(k) for k in keys]), traj=np.stack(traj),
+                            losses=np.stack(losses), target=target[0].numpy(), decay=0.75, max_step=0.1,
+                            final_max_step=opt.optimizer.max_step, **extra)
+        print('wrote', name, 'losses', np.stack(losses).min(axis=1))
+
+
 def main():
     sel = sys.argv[1:]
     os.makedirs(os.path.join(GOLD, 'grids'), exist_ok=True)
@@ -418,6 +518,7 @@ def main():
     grad_cases(sel)
     headline_cases(sel)
     ident_range_grad_case(sel)
+    optimizer_cases(sel)
 
 
 if __name__ == '__main__':
