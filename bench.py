@@ -310,6 +310,116 @@ def workload_config(P, n_gpus, note=None, variant='headline', n_rec=10):
     return cfg
 
 
+C4_SIMS = 16384
+
+
+def run_c4(args, real_stdout):
+    """--config c4: BASELINE.json configs[3] -- one parameter-identification step on the IBB model: forward + adjoint
+    gradients of the per-trajectory MSE against the reference's golden trajectory with respect to per-sim H, D, X_d' (16 384
+    trajectories sharded by rows over N GPUs) plus one parameter shared by all trajectories, whose gradient is all-reduced
+    over NCCL; the per-sim loss vector is all-gathered (arg-min of ps_optimization.py:202).  Timed twice: the eager step
+    (Python prologue + autograd around the kernels) and the same step replayed from one captured CUDA graph."""
+    import torch
+    import torch.distributed as dist
+    from diffpssi_b200 import Pss, GraphedStep, engine, sharding
+    from tests import helpers
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    engine.load_library()
+    P_total = args.sims if args.sims != P_GLOBAL else C4_SIMS
+    lo, hi = rank * P_total // world, (rank + 1) * P_total // world
+    P = hi - lo
+    rng = np.random.RandomState(0)
+    params = {('Gen 1', 'h'): 3.5 * rng.uniform(0.5, 2, P_total), ('Gen 1', 'd'): rng.uniform(0, 2, P_total),
+              ('Gen 1', 'x_d_t'): 0.3 * rng.uniform(0.5, 2, P_total)}
+    target = torch.from_numpy(np.load(os.path.join(helpers.GOLD, 'ref_ibb_model.npy'))).to(dev)
+    sim = Pss(parallel_sims=P, sim_time=T_STEPS * DT, time_step=DT, solver='heun', grid_data=helpers.load_grid('ibb'),
+              verbose=False, device=dev)
+    sim.add_sc_event(1, 1.05, 'Bus 1')
+    leaves = helpers.apply_overrides(sim, {k: v[lo:hi] for k, v in params.items()}, requires_grad=True)
+    shared = torch.tensor([[0.07 + 0j]], dtype=torch.complex128, device=dev, requires_grad=True)
+    sim.get_generator_by_name('Gen 1').t_q0_st = shared
+    sim.set_record_channels(['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'])
+    every = list(leaves.values()) + [shared]
+
+    def step():
+        for l in every:
+            l.grad = None
+        sim.reset()
+        _, res = sim.run()
+        loss = ((res - target[None]) ** 2).mean(dim=(1, 2))
+        loss.sum().backward()
+        return loss.detach()
+
+    def collectives(loss):
+        full = sharding.all_gather_rows(loss, P_total)
+        sharding.all_reduce_shared_grads([shared])
+        return full
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            full = collectives(fn())
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / n * 1e3
+        t = torch.tensor([wall, e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), full
+
+    graphed = GraphedStep(step, warmup=0)       # every execution of step() goes through its private stream (see GraphedStep.eager)
+    for _ in range(max(args.warmup, 3)):
+        collectives(graphed.eager())
+    eager_ms, eager_dev_ms, full_eager = timed(graphed.eager, args.steps)
+    grads_eager = [l.grad.clone() for l in every]
+    for _ in range(3):
+        collectives(graphed())
+    graph_ms, graph_dev_ms, full_graph = timed(graphed, args.steps)
+    same = bool(torch.equal(torch.nan_to_num(full_eager), torch.nan_to_num(full_graph))) and all(
+        bool(torch.equal(torch.nan_to_num(torch.view_as_real(a)), torch.nan_to_num(torch.view_as_real(l.grad))))
+        for a, l in zip(grads_eager, every))
+    if rank == 0:
+        line = {
+            'metric': 'sim-steps/sec (parallel_sims x steps) IBB identification step (forward + adjoint) Heun fp64',
+            'value': P_total * T_STEPS / (graph_ms * 1e-3), 'unit': 'sim-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': graph_ms, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': "BASELINE configs[3]: IBB, Heun, T=2000, forward + discrete adjoint of the per-sim trajectory "
+                                   "MSE w.r.t. per-sim H, D, X_d' and one shared parameter; loss all-gather + NCCL all-reduce of "
+                                   "the shared gradient every step", 'parallel_sims': P_total,
+                       'parallelism': 'dp%d (rows)' % world, 'step': 'one captured CUDA graph per rank (prologue, '
+                       'dps_network_reduce, dps_forward, loss, dps_backward, prologue backward) + 2 collectives'},
+            'graphed': {'ms_per_step': graph_ms, 'device_ms_per_step': graph_dev_ms},
+            'eager': {'ms_per_step': eager_ms, 'device_ms_per_step': eager_dev_ms,
+                      'sim_steps_per_s': P_total * T_STEPS / (eager_ms * 1e-3)},
+            'graph_equals_eager': same,
+            'best_row': int(torch.argmin(torch.nan_to_num(full_graph, nan=float('inf')))),
+            'shared_grad': float(shared.grad.real),
+            'gpu_launches': None,
+        }
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -321,6 +431,8 @@ def main():
     ap.add_argument('--variant', default='headline', choices=('headline', 'generic'),
                     help="'generic': distinct controller constants per generator + omega/delta recorder (no specialised kernel)")
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--config', default='c3', choices=('c3', 'c4'),
+                    help="'c3' (default): the headline IEEE-39 loop; 'c4': the IBB identification step (forward + adjoint + NCCL)")
     args = ap.parse_args()
     # the JSON line must be the only thing on stdout: libraries (NCCL prints its version with printf) get stderr
     sys.stdout.flush()
@@ -328,6 +440,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference_arm(args, real_stdout)
+    if args.config == 'c4':
+        return run_c4(args, real_stdout)
 
     import torch
     import torch.distributed as dist

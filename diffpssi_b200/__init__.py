@@ -6,7 +6,7 @@
 from .components import (Bus, Line, Transformer, Load, Shunt, SynchMachine, SEXS, TGOV1, STAB1,  # noqa: F401
                          ScEvent, ParamEvent, PIController)
 from .pss import PowerSystemSimulation, Pss  # noqa: F401
-from .optimization import PowerSystemOptimization, CustomBFGSREALOptimizer  # noqa: F401
+from .optimization import PowerSystemOptimization, CustomBFGSREALOptimizer, GraphedStep  # noqa: F401
 from . import engine  # noqa: F401
 
 __version__ = '0.1.0'

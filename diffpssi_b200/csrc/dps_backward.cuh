@@ -192,7 +192,10 @@ dps_adjoint_kernel(const BwdParams p) {
         const int k0 = ck * C;
         const int k1 = (k0 + C < p.n_steps) ? (k0 + C) : p.n_steps;
         // ---- re-integrate the segment, keeping the state at the start of every step ----------------------------------
-        {
+        // (ckpt_stride 1: the forward pass stored the state before EVERY step -- nothing to re-integrate, no scratch; the
+        // sweep reads the checkpoints directly.  A quarter of the adjoint's arithmetic and its HBM round trip go away, for
+        // n_steps x n_gen x 13 x P x 8 bytes of checkpoints, which Pss chooses when that fits comfortably.)
+        if (C > 1) {
             double x[NS], xs[NS], acc[NS], f[NSG];
             const double* src = p.ckpt + (((long long)ck * p.n_gen + g) * NSG) * P + s;
 #pragma unroll
@@ -248,11 +251,21 @@ dps_adjoint_kernel(const BwdParams p) {
         for (int step = k1 - 1; step >= k0; --step) {
             const int cfg = cfg_of(step);
             double X[4][NS], sds[4], cds[4], vres[4], vims[4];
-            {
+            if (C > 1) {
                 const double* src = p.scratch + (((long long)(step - k0) * NS) * P + s) * p.n_gen + g;
                 const long long ks = P * p.n_gen;
 #pragma unroll
                 for (int k = 0; k < NS; ++k) X[0][k] = src[k * ks];
+            } else {
+                const double* src = p.ckpt + (((long long)step * p.n_gen + g) * NSG) * P + s;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) X[0][k] = __ldcs(src + (long long)k * P);      // read once: streaming
+                // the state of the step the sweep visits next is fetched now and consumed a whole step later
+                if (step > 0) {
+                    const double* nxt = src - (long long)p.n_gen * NSG * P;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (long long)k * P));
+                }
             }
             // recorded post-step states: rec[.., step] = x_{step+1}
             if (live && rec_mask) {

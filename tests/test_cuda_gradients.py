@@ -13,10 +13,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('case,grid', CASES)
-@pytest.mark.parametrize('stride', [32, 7])
+@pytest.mark.parametrize('stride', [32, 7, 1, None])
 def test_adjoint_matches_reference_autograd(case, grid, stride):
     sim, gold, leaves = helpers.sim_from_gold(case, grid, device='cuda', requires_grad=True)
-    sim.ckpt_stride = stride                      # 7 does not divide the step count: ragged last segment
+    sim.ckpt_stride = stride       # 7 does not divide the step count (ragged last segment); 1 = every step kept, no
+                                   # re-integration in the adjoint; None = Pss chooses (1 for these sizes)
     names = [str(s) for s in gold['names']]
     _, result = sim.run()
     loss = loss_of(result.cpu(), gold, names)

@@ -29,7 +29,7 @@ else:
 sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver='heun', grid_data=grid, verbose=False)
 sim.add_sc_event(*ev)
 leaves = helpers.apply_overrides(sim, ov, requires_grad=True)
-sim.ckpt_stride = int(os.environ.get('CKPT', sim.ckpt_stride))
+sim.ckpt_stride = int(os.environ['CKPT']) if 'CKPT' in os.environ else None      # None: Pss picks (1 when it fits)
 sim.set_record_channels(chans)
 
 def sync(): torch.cuda.synchronize()
@@ -47,7 +47,7 @@ for it in range(3):
     _, res = sim.run(); sync(); t1 = time.perf_counter()
     loss = (res ** 2).mean(dim=(1, 2)).sum(); sync(); t2 = time.perf_counter()
     loss.backward(); sync(); t3 = time.perf_counter()
-print('ckpt_stride %d ' % sim.ckpt_stride, end='')
+print('ckpt_stride %s -> %d ' % (sim.ckpt_stride, sim.last_plan.topo['ckpt_stride']), end='')
 print('%s P=%d T=%d: run() %.1f ms (prologue %.1f), loss %.1f ms, backward() %.1f ms of which dps_backward (+alloc/scatter) %.1f ms'
       % (which, P, T, (t1 - t0) * 1e3, sim.timings['prologue_s'] * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, times['dps_backward_ms']))
 with torch.no_grad():
