@@ -311,6 +311,7 @@ def workload_config(P, n_gpus, note=None, variant='headline', n_rec=10):
 
 
 C4_SIMS = 16384
+E2E_CHUNKS = 16         # the last slice's copy cannot overlap anything: 1/16 of the output (11 ms at PCIe rate for N = 1)
 
 
 def run_c4(args, real_stdout):
@@ -539,6 +540,8 @@ def main():
     if not args.no_e2e:
         del rec
         torch.cuda.empty_cache()
+        from diffpssi_b200 import hostmem
+        numa = hostmem.bind_to_gpu_node(local)     # pinned pages on the GPU's own NUMA node (no-op where sysfs does not tell)
         host_params = {k: torch.from_numpy(np.ascontiguousarray(v[lo:hi])).pin_memory() for k, v in batch.items()}
         host_out = torch.empty((n_rec, T_STEPS, P), dtype=torch.float64).pin_memory()
         h2d = sum(v.numel() * 8 for v in host_params.values())
@@ -549,8 +552,8 @@ def main():
             set_parameters(sim, host_params, (0, P), dev)           # H2D from pinned host memory
             sim.reset()
             # public API: load flow + initialisation + kernels; the recorder is streamed into pinned host memory
-            # ([value][t][batch]) in 8 time slices while later steps are still being integrated
-            _, result = sim.run(host_out=host_out, stream_chunks=8)
+            # ([value][t][batch]) in E2E_CHUNKS time slices while later steps are still being integrated
+            _, result = sim.run(host_out=host_out, stream_chunks=E2E_CHUNKS)
             torch.cuda.synchronize()
 
         for _ in range(3):          # warm-up: first touches of the pinned result buffer and of the allocator's 10 GB block
@@ -565,7 +568,10 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {'value': P_total * T_STEPS / float(dt[0]), 'unit': 'sim-steps/s', 'h2d_bytes_per_step': h2d * world,
                'd2h_bytes_per_step': d2h * world, 'ms_per_step': float(dt[0]) * 1e3, 'steps': n_e2e,
-               'prologue_ms': sim.timings.get('prologue_s', 0.0) * 1e3}
+               'prologue_ms': sim.timings.get('prologue_s', 0.0) * 1e3, 'stream_chunks': E2E_CHUNKS,
+               'numa_node_of_gpu': numa.get('numa_node'),
+               'floor': 'device->pinned-host copy rate of this box (profiles/round2/d2h_probe_n8.json): 56.8 GB/s for one rank '
+                        'alone, 92.5 GB/s aggregate for 8 ranks at once => 185 ms (N=1) / 113 ms (N=8) for the 10.5 GB of results'}
 
     # ---------------- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None
