@@ -1,8 +1,9 @@
 // dps_forward_pair.cuh -- the stepping kernel with TWO trajectories per thread (sm_100a), a specialisation of
 // dps_step_kernel (dps_forward.cuh) for its hot configuration:
 //
-//   all three controllers on every generator with common, batch-uniform constants (plan pmode 3), network shared by the
-//   batch, Heun or Euler, regular recorder with a compile-time field mask, no extra observed buses, no checkpoints, and
+//   all three controllers on every generator with batch-uniform constants (common to all generators: plan pmode 3,
+//   constant-bank operands; or per generator: pmode 1, shared-memory table), network shared by the batch, Heun or Euler,
+//   regular recorder over states (omega only: compile-time mask), no extra observed buses, no checkpoints, and
 //   only the "identification" constants (1/(2H), D, the two X_d' differences, p_m0, e_fd0, v_set, bias, p_ref) differing
 //   between trajectories.
 //
@@ -95,15 +96,22 @@ struct PairCfg {
     static constexpr int MIN_BLOCKS = DPS_PAIR_MIN_BLOCKS;
 };
 
-template <int G, int SOLVER, int RMASK, bool QUEUED = false>
+// PMODE 3: controller constants common to all generators, constant-bank operands (the headline configuration).
+// PMODE 1: per-generator (batch-uniform) controller constants from a shared-memory table -- both trajectories of a thread
+//          share every load, which is what keeps this "generic" path within reach of the specialised one: in
+//          dps_step_kernel the 24 extra LDS per stage saturate the shared-memory pipe (47.6 ms against 34.1 ms).
+// RMASK >= 0: compile-time recorder mask; -1: run-time mask over the 13 states of the regular recorder layout.
+template <int G, int SOLVER, int RMASK, bool QUEUED = false, int PMODE = 3>
 __global__ void __launch_bounds__(PairCfg<G>::THREADS, PairCfg<G>::MIN_BLOCKS)
 dps_step_pair_kernel(const FwdParams p) {
     using C = PairCfg<G>;
     constexpr int SPW = C::SPW, NS = DPS_N_STATES, CM = 7;
+    constexpr int UPS = DPS_N_SLOTS + 1;           // odd row stride: the generator rows of a warp fall into distinct banks
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_zr = reinterpret_cast<double*>(smem_raw);                               // [n_cfg][col j][row g]
     double* s_zi = s_zr + p.n_cfg * G * G;
     double2* s_cur = reinterpret_cast<double2*>(s_zi + p.n_cfg * G * G);              // [WARPS][2 buffers][2 trajectories][32]
+    double* s_upar = reinterpret_cast<double*>(s_cur + C::WARPS * 128);               // PMODE 1: [G][UPS]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -116,6 +124,12 @@ dps_step_pair_kernel(const FwdParams p) {
     __shared__ int s_item;                         // work queue: the item this block is processing
 
     for (int i = threadIdx.x; i < C::WARPS * 128; i += blockDim.x) s_cur[i] = make_double2(0.0, 0.0);
+    if (PMODE == 1) {
+        for (int i = threadIdx.x; i < G * DPS_N_SLOTS; i += blockDim.x) {
+            const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
+            s_upar[gi * UPS + k] = (gi < p.n_gen) ? p.upar[i] : 0.0;
+        }
+    }
     for (int i = threadIdx.x; i < p.n_cfg * G * G; i += blockDim.x) {
         const int row = i % G, col = (i / G) % G, cfg = i / (G * G);
         const bool ok = row < p.n_gen && col < p.n_gen;
@@ -163,7 +177,8 @@ dps_step_pair_kernel(const FwdParams p) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) pm[u][k] = (vi >= 0) ? __ldg(p.vpar + (long long)vi * P + s[u]) : uni;
     }
-    const ParamPair par[2] = {{pm[0], sh, p.cpar}, {pm[1], sh, p.cpar}};
+    const double* ctrl_consts = (PMODE == 1) ? (s_upar + g * UPS) : p.cpar;
+    const ParamPair par[2] = {{pm[0], sh, ctrl_consts}, {pm[1], sh, ctrl_consts}};
 
     double x[2][NS];
 #pragma unroll
@@ -181,10 +196,11 @@ dps_step_pair_kernel(const FwdParams p) {
     const double* zcol_i = s_zi + cfg * G * G + gl;
 
     // recorder: one running pointer per recorded field; the thread's two trajectories are adjacent in every row
-    constexpr int N_RUN = __builtin_popcount((unsigned)RMASK & 0x1FFFu);
+    constexpr int N_RUN = (RMASK >= 0) ? __builtin_popcount((unsigned)RMASK & 0x1FFFu) : 0;
     const long long rec_cs = (long long)p.n_steps * P;
     double* rec_run[N_RUN > 0 ? N_RUN : 1];
-    {
+    double* rec_row = p.rec + (long long)g * rec_cs + (long long)step_begin * P + sim0;   // RMASK < 0: channel g, this step
+    if (RMASK >= 0) {
         int q = 0;
 #pragma unroll
         for (int k = 0; k < DPS_N_STATES; ++k)
@@ -269,7 +285,7 @@ dps_step_pair_kernel(const FwdParams p) {
 #pragma unroll
                 for (int k = 0; k < NS; ++k) x[u][k] = fma(f[u][k], hdt, x[u][k]);
         }
-        {
+        if (RMASK >= 0) {
             int q = 0;
 #pragma unroll
             for (int k = 0; k < DPS_N_STATES; ++k)
@@ -279,6 +295,16 @@ dps_step_pair_kernel(const FwdParams p) {
                     rec_run[q] += P;
                     ++q;
                 }
+        } else {
+            const unsigned um = p.rec_umask;           // launch-uniform: the tests below do not diverge
+#pragma unroll
+            for (int k = 0; k < DPS_N_STATES; ++k)
+                if (um & (1u << k)) {
+                    double* o = rec_row + (long long)p.rec_fbase[k] * rec_cs;
+                    if (live[0]) dps_rec_store(o, x[0][k]);
+                    if (live[1]) dps_rec_store(o + 1, x[1][k]);
+                }
+            rec_row += P;
         }
     }
 
@@ -305,20 +331,21 @@ dps_step_pair_kernel(const FwdParams p) {
 // Can this launch use the pair kernel?  (see the header comment)
 template <int G>
 static bool pair_kernel_applies(const FwdParams& p, int cmask, int pmode, long long min_sims) {
-    if (cmask != 7 || pmode != 3 || p.z_per_sim || p.ckpt_stride > 0 || p.n_obs != p.n_gen) return false;
+    if (cmask != 7 || (pmode != 3 && pmode != 1) || p.z_per_sim || p.ckpt_stride > 0 || p.n_obs != p.n_gen) return false;
     if (p.solver != DPS_HEUN && p.solver != DPS_EULER) return false;
-    if (!p.rec_regular || p.rec_umask != 0x1u || p.P < min_sims) return false;
+    // regular recorder over states only (algebraics are recorded by dps_step_kernel)
+    if (!p.rec_regular || p.rec_umask == 0u || (p.rec_umask >> DPS_N_STATES) != 0u || p.P < min_sims) return false;
     for (int g = 0; g < p.n_gen; ++g)
         for (int k = 0; k < DPS_N_REG_SLOTS; ++k)
             if (!dps_pair_reg_slot(k) && p.slot_vary[g * DPS_N_SLOTS + k] >= 0) return false;
     return true;
 }
 
-template <int G, int SOLVER>
+template <int G, int SOLVER, int RMASK, int PMODE>
 static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, int* regs) {
     using C = PairCfg<G>;
-    auto kern = dps_step_pair_kernel<G, SOLVER, 0x1, false>;
-    auto kern_q = dps_step_pair_kernel<G, SOLVER, 0x1, true>;
+    auto kern = dps_step_pair_kernel<G, SOLVER, RMASK, false, PMODE>;
+    auto kern_q = dps_step_pair_kernel<G, SOLVER, RMASK, true, PMODE>;
     if (regs) {
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, kern);
@@ -326,7 +353,8 @@ static cudaError_t launch_pair_solver(const FwdParams& p, cudaStream_t stream, i
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = sizeof(double) * p.n_cfg * G * G * 2 + sizeof(double2) * C::WARPS * 128;
+    const size_t smem = sizeof(double) * p.n_cfg * G * G * 2 + sizeof(double2) * C::WARPS * 128 +
+                        (PMODE == 1 ? sizeof(double) * G * (DPS_N_SLOTS + 1) : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -356,8 +384,14 @@ bool try_pair_kernel(const FwdParams& p, int cmask, int pmode, cudaStream_t stre
     const long long min_sims = env ? atoll(env) : 8192;
     if (!pair_kernel_applies<G>(p, cmask, pmode, min_sims)) return false;
     if (spb) *spb = PairCfg<G>::WARPS * PairCfg<G>::SPW * 2;
-    *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN>(p, stream, regs)
-                                  : launch_pair_solver<G, DPS_EULER>(p, stream, regs);
+    // two builds: the headline specialisation (common constants in the constant bank, omega recorder folded in) and the
+    // general one (per-generator constants from shared memory, run-time recorder mask) for everything else that applies
+    if (pmode == 3 && p.rec_umask == 0x1u)
+        *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN, 0x1, 3>(p, stream, regs)
+                                      : launch_pair_solver<G, DPS_EULER, 0x1, 3>(p, stream, regs);
+    else
+        *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN, -1, 1>(p, stream, regs)
+                                      : launch_pair_solver<G, DPS_EULER, -1, 1>(p, stream, regs);
     return true;
 }
 

@@ -482,3 +482,27 @@ def test_work_queue_matches_static_launch(monkeypatch, pair_min):
         out[rounds] = res.clone()
         assert bool(torch.isfinite(res).all())
     assert torch.equal(out['0'], out['12']) and torch.equal(out['0'], out['40'])
+
+
+def test_generic_pair_kernel_matches_single_trajectory_kernel(monkeypatch):
+    """The general build of dps_step_pair_kernel (per-generator controller constants from shared memory, run-time recorder
+    mask) on bench.py's ``--variant generic`` grid (distinct controller settings per machine, omega + delta recorder)
+    against dps_step_kernel on the same ragged batch, and against the C oracle."""
+    import bench
+    rng = np.random.RandomState(23)
+    P = 83
+    batch = {k: v[:P] for k, v in bench.parameter_batch(4096).items()}
+    out = {}
+    for name, min_sims in (('pair', '0'), ('single', '999999999')):
+        monkeypatch.setenv('DPS_PAIR_MIN_SIMS', min_sims)
+        sim = bench.build_sim(P, 'cuda', (0, P), batch, variant='generic')
+        _, res = sim.run()
+        out[name] = res.clone()
+        info = sim.last_plan.info()
+        assert (info['regs_per_thread'] > 200) == (name == 'pair'), info
+    assert tuple(out['pair'].shape) == (P, bench.T_STEPS, 20)
+    assert float((out['pair'] - out['single']).abs().max()) < 1e-12
+    ref = helpers.run_oracle_for(sim, sim.last_init, rec_channels=[(0, g, 0) for g in range(10)] + [(0, g, 1) for g in range(10)],
+                                 full=False)
+    want = ref['rec'].transpose(2, 1, 0)
+    _per_row_parity(out['pair'].cpu().numpy(), want, want[:, :, 10:])
