@@ -66,7 +66,8 @@ static cudaError_t plan_work_queue(FwdParams& q, const void* kern, int threads, 
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return e;
-    const long long slots = (long long)sms * per_sm;
+    long long slots = (long long)sms * per_sm;
+    if (const char* es = getenv("DPS_QUEUE_SLOTS")) slots = atoll(es);   // tests: exercise the queue at CI batch sizes
     if (slots < 1 || groups <= slots) return cudaSuccess;     // one wave: everything is resident at once anyway
     long long n_chunks = ((long long)rounds * slots + groups - 1) / groups;
     if (n_chunks < 2) return cudaSuccess;                      // many waves: the tail is already a small fraction

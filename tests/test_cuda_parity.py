@@ -506,3 +506,32 @@ def test_generic_pair_kernel_matches_single_trajectory_kernel(monkeypatch):
                                  full=False)
     want = ref['rec'].transpose(2, 1, 0)
     _per_row_parity(out['pair'].cpu().numpy(), want, want[:, :, 10:])
+
+
+@pytest.mark.parametrize('pair_min', ['0', '999999999'])
+def test_work_queue_at_small_batch(monkeypatch, pair_min):
+    """The queue forced at a CI batch size (DPS_QUEUE_SLOTS pretends the GPU holds 2 blocks): many chunks per group, ragged
+    last group, faults crossing chunk boundaries, and dps_forward_range launches on top (streamed recorder)."""
+    from diffpssi_b200 import grids
+    rng = np.random.RandomState(41)
+    P = 131
+    ov = {(g, 'h'): h * rng.uniform(0.7, 1.5, P) for g, (h, _x) in grids.GENERATOR_NOMINALS['ieee39'].items()}
+    monkeypatch.setenv('DPS_PAIR_MIN_SIMS', pair_min)
+    out = {}
+    for slots in (None, '2'):
+        if slots:
+            monkeypatch.setenv('DPS_QUEUE_SLOTS', slots)
+        else:
+            monkeypatch.delenv('DPS_QUEUE_SLOTS', raising=False)
+        sim = _ieee39_sim(P, ov, T=700)
+        sim.sc_events = []
+        sim.add_sc_event(0.3, 0.7, 'B16')
+        sim.add_sc_event(1.5, 1.6, 'B4')
+        _, res = sim.run()
+        out[slots] = res.clone()
+        if slots:
+            sim.reset()
+            host = torch.empty((10, 700, P), dtype=torch.float64).pin_memory()
+            _, streamed = sim.run(host_out=host, stream_chunks=3)
+            assert torch.equal(streamed, res.cpu())
+    assert torch.equal(out[None], out['2'])
