@@ -421,6 +421,90 @@ def run_c4(args, real_stdout):
         dist.destroy_process_group()
 
 
+def run_c5(args, real_stdout):
+    """--config c5: BASELINE.json configs[4] -- synthetic tiled 500-bus / 100-generator grid (diffpssi_b200.grids.tiled), all
+    three controllers on every machine, RK4, 8192 trajectories x 2000 steps, per-sim H / D / X_d' from the 0.5x..2x range,
+    one fault at a load bus, omega of the 100 generators recorded.  The network product V = Z I is 84 % of the flops here
+    and runs on the FP64 MMA instruction (dps_step_wide_kernel).  Rows sharded over N GPUs like config 3."""
+    import torch
+    import torch.distributed as dist
+    from diffpssi_b200 import Pss, grids, engine
+    from tests import helpers
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    engine.load_library()
+    P_total = args.sims if args.sims != P_GLOBAL else 8192
+    lo, hi = rank * P_total // world, (rank + 1) * P_total // world
+    P, T, n_cells = hi - lo, T_STEPS, 100
+    rng = np.random.RandomState(0)
+    sim = Pss(parallel_sims=P, sim_time=T * DT, time_step=DT, solver='rk4', grid_data=grids.tiled(n_cells), verbose=False,
+              device=dev)
+    sim.add_sc_event(1.0, 1.1, 'A3')
+    ov = {}
+    for c in range(n_cells):
+        ov[('M%d' % c, 'h')] = ((6.5 if c % 2 == 0 else 6.175) * rng.uniform(0.5, 2, P_total))[lo:hi]
+        ov[('M%d' % c, 'd')] = rng.uniform(0, 2, P_total)[lo:hi]
+        ov[('M%d' % c, 'x_d_t')] = (0.3 * rng.uniform(0.5, 2, P_total))[lo:hi]
+    helpers.apply_overrides(sim, ov)
+    sim.set_record_channels(['M%d.omega' % c for c in range(n_cells)])
+    prep = sim.prepare()
+    rec = torch.empty((n_cells, T, P), dtype=torch.float64, device=dev)
+    xf = torch.empty((n_cells, engine.N_STATES, P), dtype=torch.float64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        prep.launch(rec, xf)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        prep.launch(rec, xf)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    flops = 4 * n_cells * (51 + 2 + 15 + 21 + 17 + 8 * n_cells) + 14 * 13 * n_cells      # SURVEY.md 8(d): 380 600 per sim-step
+    dfma_tf, _ = engine.fp64_peak_probe(8192)
+    dmma_tf, _ = engine.fp64_dmma_probe(4096)
+    achieved = flops * P * T / (ms * 1e-3) / 1e12
+    if rank == 0:
+        line = {'metric': 'sim-steps/sec (parallel_sims x steps) tiled 500-bus / 100-gen RK4 fp64', 'value': P_total * T / (ms * 1e-3),
+                'unit': 'sim-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'BASELINE configs[4]: tiled 500-bus / 100-generator grid (SEXS+TGOV1+STAB1 on every machine), '
+                                       'RK4, dt=5 ms, T=2000, fault at load bus A3, recorder = omega of 100 generators',
+                           'parallel_sims': P_total, 'parallelism': 'dp%d (rows)' % world,
+                           'l2': 'recorder output (%.1f GB per step per GPU) exceeds the 126 MB L2' % (P * T * n_cells * 8 / 1e9)},
+                'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': max(dfma_tf, dmma_tf), 'unit': 'TFLOP/s',
+                             'frac': achieved / max(dfma_tf, dmma_tf), 'traffic': None, 'flops_per_sim_step': flops,
+                             'kernel': 'dps_step_wide_kernel<all controllers, rk4, FP64 MMA network product>', 'kernel_ms': ms,
+                             'peak_dfma_probe': dfma_tf, 'peak_dmma_probe': dmma_tf,
+                             'algorithmic_bytes_per_launch': 8 * n_cells * P * T},
+                'gpu_launches': 2 * args.steps, 'kernel': prep.plan.info(),
+                'finite_fraction': float(torch.isfinite(rec).double().mean()), 'clocks': clocks}
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -432,8 +516,9 @@ def main():
     ap.add_argument('--variant', default='headline', choices=('headline', 'generic'),
                     help="'generic': distinct controller constants per generator + omega/delta recorder (no specialised kernel)")
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--config', default='c3', choices=('c3', 'c4'),
-                    help="'c3' (default): the headline IEEE-39 loop; 'c4': the IBB identification step (forward + adjoint + NCCL)")
+    ap.add_argument('--config', default='c3', choices=('c3', 'c4', 'c5'),
+                    help="'c3' (default): the headline IEEE-39 loop; 'c4': the IBB identification step (forward + adjoint + NCCL); "
+                         "'c5': the tiled 500-bus / 100-generator RK4 run (FP64-MMA network product)")
     args = ap.parse_args()
     # the JSON line must be the only thing on stdout: libraries (NCCL prints its version with printf) get stderr
     sys.stdout.flush()
@@ -443,6 +528,8 @@ def main():
         return run_reference_arm(args, real_stdout)
     if args.config == 'c4':
         return run_c4(args, real_stdout)
+    if args.config == 'c5':
+        return run_c5(args, real_stdout)
 
     import torch
     import torch.distributed as dist

@@ -45,9 +45,10 @@ struct WideMmaGeom {
         KP = KT * 4 + (((KT * 4) % 8 == 0) ? 4 : 0);         // == 4 (mod 8): conflict-free B-fragment loads
         VS = NT * 8 + 1;
     }
-    __host__ __device__ size_t bytes(int G) const {
-        return sizeof(double) * ((size_t)2 * MT * KT * 32 + (size_t)2 * NT * 8 * KP + (size_t)MT * 8 * VS +
-                                 (size_t)G * (DPS_N_SLOTS + 1));
+    // split = true (PMODE 3): two voltage buffers (one per half of the k range), no constant table in shared memory
+    __host__ __device__ size_t bytes(int G, bool split) const {
+        return sizeof(double) * ((size_t)2 * MT * KT * 32 + (size_t)2 * NT * 8 * KP + (size_t)(split ? 2 : 1) * MT * 8 * VS +
+                                 (split ? 0 : (size_t)G * (DPS_N_SLOTS + 1)));
     }
 };
 
@@ -70,7 +71,26 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     double* s_ai = s_ar + mg.MT * mg.KT * 32;                                     // ... of Z_im
     double* s_b = s_ai + mg.MT * mg.KT * 32;                                      // [2][NT*8][KP] currents, row n = column of B
     double* s_v = s_b + 2 * mg.NT * 8 * mg.KP;                                    // [MT*8][VS] voltages
-    if (MMA) s_upar = s_v + mg.MT * 8 * mg.VS;
+    // PMODE 3 needs no constant table in shared memory (the controller constants are constant-bank operands, the machine
+    // constants are read once into registers): the room goes to a second voltage buffer, so that an output tile can be
+    // split over two warps (halves of the k range) without atomics
+    // Two experiments of round 2, kept behind switches because they document what does NOT bound this kernel (config 5,
+    // tools/gpu_wide_ab.sh, profiles/round2/wide_ab.txt): balancing the 13 output tiles over the four schedulers by splitting
+    // every tile's k range over two warps (DPS_WIDE_SPLIT: 402.7 -> 429.5 ms: the second voltage buffer, its reads and the
+    // shorter MMA chains cost more than the imbalance) and applying the sign of -I_im to the finished sums instead of to
+    // every B fragment (DPS_WIDE_SIGN_ON_SUM: 75 integer instructions fewer per tile, 404.2 ms: no effect).
+#ifndef DPS_WIDE_SPLIT
+#define DPS_WIDE_SPLIT 0
+#endif
+#ifndef DPS_WIDE_SIGN_ON_SUM
+#define DPS_WIDE_SIGN_ON_SUM 0
+#endif
+#ifndef DPS_WIDE_UNROLL
+#define DPS_WIDE_UNROLL 5
+#endif
+    constexpr bool SPLIT = MMA && (PMODE == 3) && (DPS_WIDE_SPLIT != 0);
+    constexpr int WIDE_UNROLL = DPS_WIDE_UNROLL;
+    if (MMA) s_upar = s_v + (SPLIT ? 2 : 1) * mg.MT * 8 * mg.VS;
 
     const int t = threadIdx.x;
     const int sl = t / GP;                          // trajectory slot in the block
@@ -82,9 +102,11 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     const bool live = gen_live && (sim < P);
     const long long s = (sim < P) ? sim : (P - 1);
 
-    for (int i = t; i < G * DPS_N_SLOTS; i += blockDim.x) {
-        const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
-        s_upar[gi * UPS + k] = p.upar[i];
+    if (!SPLIT) {
+        for (int i = t; i < G * DPS_N_SLOTS; i += blockDim.x) {
+            const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
+            s_upar[gi * UPS + k] = p.upar[i];
+        }
     }
     auto load_z = [&](int cfg) {
         if (MMA) {
@@ -100,6 +122,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             }
             // padding columns of the current rows stay zero for the whole run
             for (int i = t; i < 2 * mg.NT * 8 * mg.KP; i += blockDim.x) s_b[i] = 0.0;
+
         } else {
             // transposed copy of configuration cfg: s_z[j*G + g] = Z[g][j]
             for (int i = t; i < G * G; i += blockDim.x) {
@@ -122,7 +145,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
 #pragma unroll
     for (int k = 0; k < DPS_N_REG_SLOTS; ++k) {
         const int vi = p.reg_vary[g][k];
-        pm[k] = (vi >= 0) ? __ldg(p.vpar + (long long)vi * P + s) : up[k];
+        pm[k] = (vi >= 0) ? __ldg(p.vpar + (long long)vi * P + s) : (SPLIT ? __ldg(p.upar + g * DPS_N_SLOTS + k) : up[k]);
     }
     ParamRegs par_fast{pm, up};
     ParamConst par_const{pm, p.cpar};
@@ -162,30 +185,51 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
             __syncthreads();
             const int lane = t & 31, warp = t >> 5;
             const int fr = lane >> 2, fk = lane & 3;                     // fragment row (A) / column (B), and k index
-            for (int u = warp; u < mg.MT * mg.NT; u += WIDE_THREADS / 32) {
-                const int mt = u % mg.MT, nt = u / mg.MT;
+            // SPLIT: work units = (output tile, half of the k range): 2 MT NT units over the 16 warps, so that the four
+            // schedulers get (almost) equal shares -- 13 whole tiles gave scheduler 0 four tiles and the others three.
+            // Each half writes its own voltage buffer; the reader adds the two.
+            const int n_units = (SPLIT ? 2 : 1) * mg.MT * mg.NT;
+            const int KH = SPLIT ? (mg.KT + 1) / 2 : mg.KT;
+            for (int u = warp; u < n_units; u += WIDE_THREADS / 32) {
+                const int half = SPLIT ? (u & 1) : 0, tile = SPLIT ? (u >> 1) : u;
+                const int mt = tile % mg.MT, nt = tile / mg.MT;
+                const int k0 = half ? KH : 0, k1 = half ? mg.KT : KH;
                 const double* ar = s_ar + (mt * mg.KT) * 32 + lane;
                 const double* ai = s_ai + (mt * mg.KT) * 32 + lane;
                 const double* b1 = bcur + (nt * 8 + fr) * mg.KP + fk;              // [ I_re | I_im ]
-                const double* b2 = bcur + (nt * 8 + ((fr + 4) & 7)) * mg.KP + fk;  // [-I_im | I_re ]
-                const int flip = (fr < 4) ? (int)0x80000000 : 0;                   // sign of -I_im, applied on the integer pipe
-                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-#pragma unroll 5
-                for (int kt = 0; kt < mg.KT; ++kt) {
+                const double* b2 = bcur + (nt * 8 + ((fr + 4) & 7)) * mg.KP + fk;  // [ I_im | I_re ]: the sign of -I_im is applied
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;                     // to the finished sum (exact), not per element
+#if !DPS_WIDE_SIGN_ON_SUM
+                const int flip = (fr < 4) ? (int)0x80000000 : 0;
+#endif
+#pragma unroll WIDE_UNROLL
+                for (int kt = k0; kt < k1; ++kt) {
                     const double a_r = ar[kt * 32], a_i = ai[kt * 32];
-                    const double x1 = b1[kt * 4];
                     double x2 = b2[kt * 4];
+#if !DPS_WIDE_SIGN_ON_SUM
                     x2 = __hiloint2double(__double2hiint(x2) ^ flip, __double2loint(x2));
-                    dmma_m8n8k4(d0, d1, a_r, x1);
+#endif
+                    dmma_m8n8k4(d0, d1, a_r, b1[kt * 4]);
                     dmma_m8n8k4(e0, e1, a_i, x2);
                 }
-                double* vo = s_v + (mt * 8 + fr) * mg.VS + nt * 8 + 2 * fk;
+                // columns 0..3 of the tile are V_re = Z_re I_re - Z_im I_im, columns 4..7 V_im = Z_re I_im + Z_im I_re
+                double* vo = s_v + half * (mg.MT * 8 * mg.VS) + (mt * 8 + fr) * mg.VS + nt * 8 + 2 * fk;
+#if DPS_WIDE_SIGN_ON_SUM
+                vo[0] = (fk < 2) ? d0 - e0 : d0 + e0;
+                vo[1] = (fk < 2) ? d1 - e1 : d1 + e1;
+#else
                 vo[0] = d0 + e0;
                 vo[1] = d1 + e1;
+#endif
             }
             __syncthreads();
-            v_re = s_v[gl * mg.VS + nrow];
-            v_im = s_v[gl * mg.VS + nrow + 4];
+            // (row g, not gl: the padding lanes of the last warp would read past the voltage buffers)
+            v_re = s_v[g * mg.VS + nrow];
+            v_im = s_v[g * mg.VS + nrow + 4];
+            if (SPLIT) {
+                v_re += s_v[mg.MT * 8 * mg.VS + g * mg.VS + nrow];
+                v_im += s_v[mg.MT * 8 * mg.VS + g * mg.VS + nrow + 4];
+            }
             buf ^= 1;
         } else {
         if (sl < SPB) cb[gl] = gen_live ? make_double2(i_re, i_im) : make_double2(0.0, 0.0);
@@ -305,7 +349,7 @@ static cudaError_t launch_wide_one(const WideParams& p, cudaStream_t stream, int
     const int G = p.n_gen;
     const int WG = (G + 31) / 32;
     const int SPB = WIDE_THREADS / (WG * 32);
-    const bool mma = WideMmaGeom(G, SPB).bytes(G) <= 227 * 1024 && getenv("DPS_WIDE_NO_MMA") == nullptr;
+    const bool mma = WideMmaGeom(G, SPB).bytes(G, PMODE == 3 && DPS_WIDE_SPLIT) <= 227 * 1024 && getenv("DPS_WIDE_NO_MMA") == nullptr;
     return mma ? launch_wide_kern<CM, PMODE, SOLVER, true>(p, stream, regs, threads_out, spb_out)
                : launch_wide_kern<CM, PMODE, SOLVER, false>(p, stream, regs, threads_out, spb_out);
 }
@@ -325,7 +369,7 @@ static cudaError_t launch_wide_kern(const WideParams& p, cudaStream_t stream, in
         *regs = a.numRegs;
         return cudaSuccess;
     }
-    const size_t smem = MMA ? WideMmaGeom(G, SPB).bytes(G)
+    const size_t smem = MMA ? WideMmaGeom(G, SPB).bytes(G, PMODE == 3 && DPS_WIDE_SPLIT)
                             : sizeof(double2) * ((size_t)G * G + 2 * SPB * WG * 32) + sizeof(double) * G * (DPS_N_SLOTS + 1);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
