@@ -57,9 +57,15 @@ using namespace dps;
 
 extern "C" {
 
+static size_t adjoint_scratch_bytes(const dps_plan* plan, int64_t P) {
+    return sizeof(double) * (size_t)plan->topo.ckpt_stride * plan->topo.n_gen * DPS_N_STATES * (size_t)P;
+}
+
 size_t dps_workspace_bytes(const dps_plan* plan, int64_t P) {
     if (!plan || plan->topo.ckpt_stride <= 0 || P < 1) return 0;
-    return sizeof(double) * (size_t)plan->topo.ckpt_stride * plan->topo.n_gen * DPS_N_STATES * (size_t)P;
+    // per-step state scratch of one checkpoint segment + the work-queue words (one dequeue counter, one progress word per
+    // block group; a group holds at least 8 trajectories)
+    return adjoint_scratch_bytes(plan, P) + sizeof(int) * (size_t)(P / 8 + 66);
 }
 
 int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const double* vpar, const double* zsub,
@@ -81,6 +87,9 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     p.P = P; p.n_gen = b.n_gen; p.solver = b.solver; p.n_steps = b.n_steps; p.dt = b.dt; p.fn = b.fn;
     p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.ckpt = ckpt; p.grad_rec = grad_rec; p.grad_xf = grad_x_final;
     p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = g_zsub; p.scratch = (double*)workspace;
+    p.q_counter = (int*)((char*)workspace + adjoint_scratch_bytes(plan, P));
+    p.q_progress = p.q_counter + 1;
+    p.q_capacity = (int)(P / 8 + 64);
     p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.n_cfg = b.n_cfg; p.z_per_sim = b.z_per_sim;
     p.ckpt_stride = b.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
     p.fast_par = (plan->pmode != 2) ? 1 : 0;
@@ -96,7 +105,15 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     for (int i = 0; i < b.n_gen * DPS_N_SLOTS; ++i)
         if (want[i]) p.want_row[i] = (short)n_want++;
     if (n_want > 0 && !gslot) { set_error("dps_backward: slot gradients wanted but gslot is null"); return 1; }
-    if (p.n_steps == 0) return 0;
+    if (p.n_steps == 0) {
+        // nothing to sweep: dL/dx0 = dL/dx_final, no slot gradient
+        cudaError_t e0 = grad_x_final ? cudaMemcpyAsync(g_x0, grad_x_final, sizeof(double) * (size_t)b.n_gen * DPS_N_STATES * P,
+                                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream)
+                                      : cudaMemsetAsync(g_x0, 0, sizeof(double) * (size_t)b.n_gen * DPS_N_STATES * P, (cudaStream_t)stream);
+        if (e0 == cudaSuccess && n_want > 0) e0 = cudaMemsetAsync(gslot, 0, sizeof(double) * (size_t)n_want * P, (cudaStream_t)stream);
+        if (e0 != cudaSuccess) { set_error("dps_backward: %s", cudaGetErrorString(e0)); return 3; }
+        return 0;
+    }
     // how many leading slots need an accumulator: 0, the register slots, or all of them
     int ngp = 0;
     for (int g = 0; g < b.n_gen; ++g)

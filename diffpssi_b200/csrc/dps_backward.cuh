@@ -2,6 +2,7 @@
 // (one translation unit per G so the build parallelises); ABI entry points and dispatch: dps_backward.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 #include "dps_internal.h"
 #include "dps_adjoint.cuh"
@@ -42,7 +43,7 @@ struct ReaderPick<false> {
     __device__ __forceinline__ static const ParamReader<true>& get(const ParamRegs&, const ParamReader<true>& b) { return b; }
 };
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
+template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR, bool QUEUED = false>
 __global__ void __launch_bounds__(BwdCfg<G>::THREADS, 2)
 dps_adjoint_kernel(const BwdParams p) {
     using Cfg = BwdCfg<G>;
@@ -72,7 +73,21 @@ dps_adjoint_kernel(const BwdParams p) {
     const bool gen_live = (sl < SPW) && (gl < p.n_gen);
     const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
-    const long long sim = ((long long)blockIdx.x * Cfg::WARPS + warp) * SPW + sl;
+    // work item (see dps_step_kernel): block group + chunk of checkpoint segments, taken by ticket
+    __shared__ int s_item;
+    long long group = blockIdx.x;
+    int chunk = 0;
+    if (QUEUED) {
+        if (threadIdx.x == 0) s_item = atomicAdd(p.q_counter, 1);
+        __syncthreads();
+        const int item = __reduce_max_sync(0xffffffffu, s_item);     // REDUX: provably warp-uniform
+        chunk = item / p.q_groups;
+        group = item - chunk * p.q_groups;
+        if (chunk > 0 && threadIdx.x == 0)
+            while (dps_ld_acquire(p.q_progress + group) < chunk) __nanosleep(100);
+        __syncthreads();
+    }
+    const long long sim = ((long long)(QUEUED ? group : (long long)blockIdx.x) * Cfg::WARPS + warp) * SPW + sl;
     const bool live = (sim < P) && gen_live;
     const long long s = (sim < P) ? sim : (P - 1);
 
@@ -176,11 +191,20 @@ dps_adjoint_kernel(const BwdParams p) {
 
     double lam[NS];
     SlotGrads<NGP> gp;
+    const short* wr = p.want_row + g * DPS_N_SLOTS;
+    if (!QUEUED || chunk == 0) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k)
-        lam[k] = (p.grad_xf != nullptr) ? p.grad_xf[((long long)g * NSG + k) * P + s] : 0.0;
+        for (int k = 0; k < NS; ++k)
+            lam[k] = (p.grad_xf != nullptr) ? p.grad_xf[((long long)g * NSG + k) * P + s] : 0.0;
 #pragma unroll
-    for (int k = 0; k < NGP; ++k) gp.v[k] = 0.0;
+        for (int k = 0; k < NGP; ++k) gp.v[k] = 0.0;
+    } else {
+        // continue where the previous chunk of this group stopped (written by another SM: read through L2)
+#pragma unroll
+        for (int k = 0; k < NS; ++k) lam[k] = __ldcg(p.g_x0 + ((long long)g * NSG + k) * P + s);
+#pragma unroll
+        for (int k = 0; k < NGP; ++k) gp.v[k] = (wr[k] >= 0) ? __ldcg(p.gslot + (long long)wr[k] * P + s) : 0.0;
+    }
     gp.dummy = 0.0;
 
     const unsigned rec_mask = p.rec_mask[g];
@@ -188,7 +212,9 @@ dps_adjoint_kernel(const BwdParams p) {
     const long long cs = (long long)p.n_steps * P;
     const int C = p.ckpt_stride;
 
-    for (int ck = p.n_ckpt - 1; ck >= 0; --ck) {
+    const int ck_hi = QUEUED ? p.n_ckpt - chunk * p.q_chunk_ckpts : p.n_ckpt;            // exclusive
+    const int ck_lo = QUEUED ? ((ck_hi - p.q_chunk_ckpts > 0) ? ck_hi - p.q_chunk_ckpts : 0) : 0;
+    for (int ck = ck_hi - 1; ck >= ck_lo; --ck) {
         const int k0 = ck * C;
         const int k1 = (k0 + C < p.n_steps) ? (k0 + C) : p.n_steps;
         // ---- re-integrate the segment, keeping the state at the start of every step ----------------------------------
@@ -379,11 +405,49 @@ dps_adjoint_kernel(const BwdParams p) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) dst[(long long)k * P] = lam[k];
         for (int k = NS; k < NSG; ++k) dst[(long long)k * P] = 0.0;
-        const short* wr = p.want_row + g * DPS_N_SLOTS;
 #pragma unroll
         for (int k = 0; k < NGP; ++k)
             if (wr[k] >= 0) p.gslot[(long long)wr[k] * P + s] = gp.v[k];
     }
+    if (QUEUED) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int item = s_item, c = item / p.q_groups;
+            dps_st_release(p.q_progress + (item - c * p.q_groups), c + 1);
+        }
+    }
+}
+
+// Work-queue planning of the adjoint (see plan_work_queue in dps_forward_pair.cuh): chunks are whole checkpoint segments.
+static cudaError_t plan_adjoint_queue(BwdParams& q, const void* kern, int threads, size_t smem, long long groups, unsigned* grid,
+                                      cudaStream_t stream) {
+    q.q_items = 0;
+    if (q.q_counter == nullptr || groups > q.q_capacity || groups > 0x3fffffff) return cudaSuccess;
+    const char* env = getenv("DPS_QUEUE_ROUNDS");
+    const int rounds = env ? atoi(env) : 12;
+    if (rounds == 0 || q.n_ckpt < 4) return cudaSuccess;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    long long slots = (long long)sms * per_sm;
+    if (const char* es = getenv("DPS_QUEUE_SLOTS")) slots = atoll(es);
+    if (slots < 1 || groups <= slots) return cudaSuccess;
+    long long n_chunks = ((long long)rounds * slots + groups - 1) / groups;
+    if (n_chunks < 2) return cudaSuccess;
+    int chunk_ckpts = (int)((q.n_ckpt + n_chunks - 1) / n_chunks);
+    if (chunk_ckpts < 1) chunk_ckpts = 1;
+    n_chunks = (q.n_ckpt + chunk_ckpts - 1) / chunk_ckpts;
+    if (n_chunks < 2 || groups * n_chunks > 0x3fffffff) return cudaSuccess;
+    q.q_items = (int)(groups * n_chunks);
+    q.q_groups = (int)groups;
+    q.q_chunk_ckpts = chunk_ckpts;
+    *grid = (unsigned)q.q_items;
+    return cudaMemsetAsync(q.q_counter, 0, sizeof(int) * (size_t)(groups + 1), stream);
 }
 
 template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
@@ -391,14 +455,30 @@ static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
     const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * G * DPS_N_SLOTS + sizeof(short) * G * DPS_N_SLOTS +
                         (p.z_per_sim ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
+    auto kern = dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, false>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long spb = (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + spb - 1) / spb;
-    dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR><<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+    // the work-queue build exists for the common case (no network gradient: those accumulate dL/dZ in HBM across chunks)
+    if constexpr (!ZGRAD && FASTPAR) {
+        auto kern_q = dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, true>;
+        BwdParams q = p;
+        unsigned grid = (unsigned)blocks;
+        cudaError_t e = plan_adjoint_queue(q, (const void*)kern_q, C::THREADS, smem, blocks, &grid, stream);
+        if (e != cudaSuccess) return e;
+        if (q.q_items > 0) {
+            if (smem > 48 * 1024) {
+                e = cudaFuncSetAttribute(kern_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            kern_q<<<grid, C::THREADS, smem, stream>>>(q);
+            return cudaGetLastError();
+        }
+    }
+    kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

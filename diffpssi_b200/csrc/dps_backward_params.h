@@ -28,6 +28,12 @@ struct BwdParams {
     short obs_chan[MAX_EXTRA_OBS][2];
     short slot_vary[MAX_G * DPS_N_SLOTS];
     short want_row[MAX_G * DPS_N_SLOTS];
+    // Work queue (q_items > 0; same scheme as the forward stepper, dps_internal.h): items = (block group, chunk of
+    // q_chunk_ckpts checkpoint segments), chunk 0 = the LAST segments of the run (the sweep walks time backwards).  The
+    // co-state and the slot-gradient accumulators of a group travel between its chunks through g_x0 / gslot.
+    int q_items, q_groups, q_chunk_ckpts, q_capacity;
+    int* q_counter;
+    int* q_progress;
 };
 
 }  // namespace dps

@@ -120,3 +120,28 @@ def test_identification_loop_reduces_the_loss():
     off = (h.detach().real.reshape(-1) - 3.5).abs() > 0.3                  # sims that did not start next to the optimum
     assert bool((last[off] < 0.5 * first[off]).all()), (first, last)
     assert float((h.detach().real.reshape(-1) - 3.5).abs().mean()) < float(np.abs(np.linspace(2.0, 6.0, P) - 3.5).mean())
+
+
+@pytest.mark.parametrize('stride', [32, 5, 1])
+def test_adjoint_work_queue_matches_static_launch(monkeypatch, stride):
+    """dps_adjoint_kernel as (block group, chunk of checkpoint segments) work items (forced at a CI batch size through
+    DPS_QUEUE_SLOTS): co-state and slot-gradient accumulators travel between the chunks through g_x0 / gslot; the gradients
+    must be bit-identical to the one-block-per-group launch."""
+    grads = {}
+    for slots in (None, '2'):
+        if slots:
+            monkeypatch.setenv('DPS_QUEUE_SLOTS', slots)
+        else:
+            monkeypatch.delenv('DPS_QUEUE_SLOTS', raising=False)
+        sim, gold, leaves = helpers.sim_from_gold('grad_k2a_heun', 'k2a', device='cuda', requires_grad=True, tile=40)
+        sim.ckpt_stride = stride
+        names = [str(s) for s in gold['names']]
+        _, result = sim.run()
+        loss = loss_of(result, gold, names)
+        loss.sum().backward()
+        grads[slots] = {k: v.grad.real.clone() for k, v in leaves.items()}
+    for k in grads[None]:
+        assert torch.equal(grads[None][k], grads['2'][k]), k
+        ref = np.tile(gold['grad/gen|%s|%s' % k], 40)
+        mine = grads['2'][k].cpu().numpy().reshape(-1)
+        assert (np.abs(mine - ref) / np.abs(ref).max()).max() < 1e-6
