@@ -44,10 +44,6 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
         set_error("dps_plan_create: systems with more than %d generators need a network shared by the batch", MAX_G);
         return 2;
     }
-    if (wide && t->ckpt_stride > 0) {
-        set_error("dps_plan_create: the adjoint is not available for systems with more than %d generators", MAX_G);
-        return 2;
-    }
     if (t->solver < DPS_EULER || t->solver > DPS_RK4) { set_error("dps_plan_create: unknown solver %d", t->solver); return 1; }
     if (t->n_steps < 0 || !(t->dt > 0.0)) { set_error("dps_plan_create: bad n_steps/dt"); return 1; }
     if (t->n_obs < t->n_gen || t->n_obs - t->n_gen > MAX_EXTRA_OBS) { set_error("dps_plan_create: n_obs out of range"); return 1; }
@@ -103,10 +99,6 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
         pl->pmode = 3;
         for (int k = 0; k < DPS_N_SLOTS; ++k) b.cpar[k] = w.cpar[k] = t->common_ctrl[k];
     }
-    if (wide && pl->pmode == 2) {
-        set_error("dps_plan_create: with more than %d generators only the machine constants and set points may differ per trajectory", MAX_G);
-        delete pl; return 2;
-    }
     b.n_gen = t->n_gen; b.solver = t->solver; b.n_steps = t->n_steps; b.dt = t->dt; b.fn = t->fn;
     b.n_obs = t->n_obs; b.z_rows = t->z_rows; b.z_cols = t->z_cols; b.n_cfg = t->n_cfg; b.z_per_sim = t->z_per_sim;
     b.ckpt_stride = t->ckpt_stride;
@@ -117,6 +109,7 @@ int dps_plan_create(const dps_topology* t, dps_plan** out) {
         if (wide) {
             w.ctrl[g] = (unsigned char)pl->ctrl[g];
             for (int k = 0; k < DPS_N_REG_SLOTS; ++k) w.reg_vary[g][k] = (short)pl->slot_vary[(size_t)g * DPS_N_SLOTS + k];
+            for (int k = 0; k < DPS_N_SLOTS; ++k) w.slot_vary[g][k] = (short)pl->slot_vary[(size_t)g * DPS_N_SLOTS + k];
         } else {
             b.ctrl[g] = pl->ctrl[g];
             for (int k = 0; k < DPS_N_SLOTS; ++k) b.slot_vary[g * DPS_N_SLOTS + k] = (short)pl->slot_vary[(size_t)g * DPS_N_SLOTS + k];

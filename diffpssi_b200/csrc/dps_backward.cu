@@ -33,6 +33,8 @@ cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, int ngp, cudaStream_t st
 DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(16)
 #undef DPS_EXTERN
 
+cudaError_t launch_bwd_wide(const BwdWideParams& p, bool ctrl, int ngp, cudaStream_t stream);
+
 static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl, int ngp, cudaStream_t stream) {
 #ifdef DPS_ONLY_G10      // kernel A/B experiment builds (tools/build_variant.sh)
     return g_template == 10 ? launch_bwd_g<10>(p, ctrl, ngp, stream) : cudaErrorInvalidValue;
@@ -55,11 +57,59 @@ static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl
 
 using namespace dps;
 
-extern "C" {
-
 static size_t adjoint_scratch_bytes(const dps_plan* plan, int64_t P) {
     return sizeof(double) * (size_t)plan->topo.ckpt_stride * plan->topo.n_gen * DPS_N_STATES * (size_t)P;
 }
+
+// 17..128 generators: same sweep, tables sized for MAX_GW, block-wide exchange (dps_backward_wide.cu)
+static int backward_wide(const dps_plan* plan, int64_t P, const double* upar, const double* vpar, const double* zsub,
+                         const double* ckpt, const double* grad_rec, const double* grad_x_final, const uint8_t* want,
+                         double* g_x0, double* gslot, void* workspace, void* stream) {
+    static thread_local BwdWideParams p;                 // ~28 KB: not on the stack of a Python thread
+    memset(&p, 0, sizeof(p));
+    const WideParams& w = plan->wbase;
+    const int G = w.n_gen;
+    p.P = P; p.n_gen = G; p.solver = w.solver; p.n_steps = w.n_steps; p.dt = w.dt; p.fn = w.fn;
+    p.upar = upar; p.vpar = vpar; p.zsub = zsub; p.ckpt = ckpt; p.grad_rec = grad_rec; p.grad_xf = grad_x_final;
+    p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = nullptr; p.scratch = (double*)workspace;
+    p.q_counter = (int*)((char*)workspace + adjoint_scratch_bytes(plan, P));
+    p.q_progress = p.q_counter + 1;
+    p.q_capacity = (int)(P / 8 + 64);
+    p.n_obs = w.n_obs; p.z_rows = w.z_rows; p.z_cols = w.z_cols; p.n_cfg = w.n_cfg; p.z_per_sim = 0;
+    p.ckpt_stride = w.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
+    p.fast_par = (plan->pmode != 2) ? 1 : 0;
+    p.n_seg = (int)plan->seg_step.size();
+    for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[i]; p.seg_cfg[i] = plan->seg_cfg[i]; }
+    for (int g = 0; g < G; ++g) {
+        p.ctrl[g] = w.ctrl[g];
+        p.rec_mask[g] = w.rec_mask[g];
+        memcpy(p.rec_chan[g], w.rec_chan[g], sizeof(p.rec_chan[g]));
+        for (int k = 0; k < DPS_N_SLOTS; ++k) p.slot_vary[g * DPS_N_SLOTS + k] = w.slot_vary[g][k];
+    }
+    memcpy(p.obs_chan, w.obs_chan, sizeof(p.obs_chan));
+    int n_want = 0;
+    for (int i = 0; i < MAX_GW * DPS_N_SLOTS; ++i) p.want_row[i] = -1;
+    for (int i = 0; i < G * DPS_N_SLOTS; ++i)
+        if (want[i]) p.want_row[i] = (short)n_want++;
+    if (n_want > 0 && !gslot) { set_error("dps_backward: slot gradients wanted but gslot is null"); return 1; }
+    if (p.n_steps == 0) {
+        cudaError_t e0 = grad_x_final ? cudaMemcpyAsync(g_x0, grad_x_final, sizeof(double) * (size_t)G * DPS_N_STATES * P,
+                                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream)
+                                      : cudaMemsetAsync(g_x0, 0, sizeof(double) * (size_t)G * DPS_N_STATES * P, (cudaStream_t)stream);
+        if (e0 == cudaSuccess && n_want > 0) e0 = cudaMemsetAsync(gslot, 0, sizeof(double) * (size_t)n_want * P, (cudaStream_t)stream);
+        if (e0 != cudaSuccess) { set_error("dps_backward: %s", cudaGetErrorString(e0)); return 3; }
+        return 0;
+    }
+    int ngp = 0;
+    for (int g = 0; g < G; ++g)
+        for (int k = 0; k < DPS_N_SLOTS; ++k)
+            if (want[g * DPS_N_SLOTS + k] && k + 1 > ngp) ngp = k + 1;
+    cudaError_t e = launch_bwd_wide(p, plan->any_ctrl, ngp, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("dps_backward: launch failed: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
+extern "C" {
 
 size_t dps_workspace_bytes(const dps_plan* plan, int64_t P) {
     if (!plan || plan->topo.ckpt_stride <= 0 || P < 1) return 0;
@@ -81,6 +131,10 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     const size_t need = dps_workspace_bytes(plan, P);
     if (!workspace || workspace_bytes < need) { set_error("dps_backward: workspace too small (%zu < %zu bytes)", workspace_bytes, need); return 1; }
 
+    if (plan->wide) {
+        if (g_zsub) { set_error("dps_backward: gradients with respect to the network are not available for more than %d generators", MAX_G); return 2; }
+        return backward_wide(plan, P, upar, vpar, zsub, ckpt, grad_rec, grad_x_final, want, g_x0, gslot, workspace, stream);
+    }
     BwdParams p;
     memset(&p, 0, sizeof(p));
     const FwdParams& b = plan->base;

@@ -15,10 +15,15 @@ namespace dps {
 // cotangents (for dI = Z^T dV) are exchanged through the warp's private shared-memory line behind a __syncwarp: no block
 // barrier, warps never wait for each other.  (Until r2p a warp held 32 trajectories of one generator and the G warps of a
 // group met at a named barrier twice per stage: one block of 10 warps per SM in lockstep, 28 % FP64-pipe activity.)
+// G = 0 selects the WIDE build (17..128 generators, run-time generator count): a trajectory occupies ceil(n_gen / 32) warps
+// of a 256-thread block, currents and voltage cotangents are exchanged through block-wide shared-memory lines behind
+// __syncthreads, and Z is read from global memory (L2-resident: 160 KB for 100 generators).  Same per-thread arithmetic
+// (dps_adjoint.cuh), same checkpoint / scratch layout, so the forward wide stepper's checkpoints feed it directly.
 template <int G>
 struct BwdCfg {
-    static constexpr int SPW = 32 / G;             // trajectories per warp
-    static constexpr int WARPS = 4;
+    static constexpr bool WIDE = (G == 0);
+    static constexpr int SPW = WIDE ? 0 : 32 / (G ? G : 1);       // trajectories per warp
+    static constexpr int WARPS = WIDE ? 8 : 4;
     static constexpr int THREADS = 32 * WARPS;
 };
 
@@ -43,34 +48,39 @@ struct ReaderPick<false> {
     __device__ __forceinline__ static const ParamReader<true>& get(const ParamRegs&, const ParamReader<true>& b) { return b; }
 };
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR, bool QUEUED = false>
-__global__ void __launch_bounds__(BwdCfg<G>::THREADS, 2)
-dps_adjoint_kernel(const BwdParams p) {
+template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR, bool QUEUED = false>
+__global__ void __launch_bounds__(BwdCfg<G>::THREADS, BwdCfg<G>::WIDE ? 1 : 2)
+dps_adjoint_kernel(const PT p) {
     using Cfg = BwdCfg<G>;
+    constexpr bool WIDE = Cfg::WIDE;
     constexpr int SPW = Cfg::SPW;
+    const int GG = WIDE ? p.n_gen : G;                            // generators (table strides)
+    const int GP = WIDE ? ((p.n_gen + 31) & ~31) : G;             // lanes a trajectory occupies
+    const int SPB = WIDE ? Cfg::THREADS / GP : Cfg::WARPS * SPW;  // trajectories per block
     // live states per generator: a bare machine (no controllers anywhere) carries 6, its 7 controller rows are zero.  The
     // per-step scratch, the register arrays and the sweep only hold NS of them; NSG is the stride of the 13-row buffers.
     constexpr int NS = CTRL ? DPS_N_STATES : 6;
     constexpr int NSG = DPS_N_STATES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s_xch = reinterpret_cast<double2*>(smem_raw);                       // [WARPS][2][32] exchange lines
+    double2* s_xch = reinterpret_cast<double2*>(smem_raw);                       // [WARPS][2][32] exchange lines (wide: [2][THREADS])
     double* s_upar = reinterpret_cast<double*>(s_xch + Cfg::WARPS * 64);         // [G][DPS_N_SLOTS]
     // network shared by the batch: Z of every configuration in shared memory, (re, im) planes, in both orientations --
     // s_zt[cfg][j][g] = Z[g][j] for V = Z I (lanes of a trajectory read consecutive doubles) and s_zn[cfg][r][g] = Z[r][g]
     // for dI = Z^T dV -- so the two products are LDS with compile-time offsets instead of pointer-chasing global loads
-    const int n_cfg_s = p.z_per_sim ? 0 : p.n_cfg;
-    double* s_ztr = s_upar + G * DPS_N_SLOTS;
+    const int n_cfg_s = (WIDE || p.z_per_sim) ? 0 : p.n_cfg;
+    double* s_ztr = s_upar + GG * DPS_N_SLOTS;
     double* s_zti = s_ztr + n_cfg_s * G * G;
     double* s_znr = s_zti + n_cfg_s * G * G;
     double* s_zni = s_znr + n_cfg_s * G * G;
     short* s_vary = reinterpret_cast<short*>(s_zni + n_cfg_s * G * G);           // [G][DPS_N_SLOTS]
 
-    const int lane = threadIdx.x & 31;
+    const int lane = WIDE ? (int)threadIdx.x : (int)(threadIdx.x & 31);          // index into the exchange line
     const int warp = threadIdx.x >> 5;
-    const int sl = lane / G;                       // trajectory slot inside the warp
-    const int gl = lane - sl * G;                  // generator slot
-    const int base = ((sl < SPW) ? sl : SPW - 1) * G;       // first lane of this trajectory's generator group
-    const bool gen_live = (sl < SPW) && (gl < p.n_gen);
+    const int sl = lane / GP;                      // trajectory slot inside the warp (wide: inside the block)
+    const int gl = lane - sl * GP;                 // generator slot
+    const int n_slots = WIDE ? SPB : SPW;
+    const int base = ((sl < n_slots) ? sl : n_slots - 1) * GP;   // first lane of this trajectory's generator group
+    const bool gen_live = (sl < n_slots) && (gl < p.n_gen);
     const int g = (gl < p.n_gen) ? gl : p.n_gen - 1;
     const long long P = p.P;
     // work item (see dps_step_kernel): block group + chunk of checkpoint segments, taken by ticket
@@ -87,19 +97,21 @@ dps_adjoint_kernel(const BwdParams p) {
             while (dps_ld_acquire(p.q_progress + group) < chunk) __nanosleep(100);
         __syncthreads();
     }
-    const long long sim = ((long long)(QUEUED ? group : (long long)blockIdx.x) * Cfg::WARPS + warp) * SPW + sl;
+    const long long grp = QUEUED ? group : (long long)blockIdx.x;
+    const long long sim = WIDE ? grp * SPB + sl : (grp * Cfg::WARPS + warp) * SPW + sl;
     const bool live = (sim < P) && gen_live;
     const long long s = (sim < P) ? sim : (P - 1);
 
-    for (int i = threadIdx.x; i < G * DPS_N_SLOTS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < GG * DPS_N_SLOTS; i += blockDim.x) {
         const bool ok = (i / DPS_N_SLOTS) < p.n_gen;
         s_upar[i] = ok ? p.upar[i] : 0.0;
         s_vary[i] = ok ? p.slot_vary[i] : (short)-1;
     }
     // exchange lines start at zero; only live generator lanes ever store (padding lanes contribute exact zeros)
     for (int i = threadIdx.x; i < Cfg::WARPS * 64; i += blockDim.x) s_xch[i] = make_double2(0.0, 0.0);
+    constexpr int GD = WIDE ? 1 : G;               // (the wide build has no shared Z tables: n_cfg_s == 0)
     for (int i = threadIdx.x; i < n_cfg_s * G * G; i += blockDim.x) {
-        const int a = i % G, b = (i / G) % G, cfg = i / (G * G);           // s_zt[cfg][b][a] = Z[a][b];  s_zn[cfg][b][a] = Z[b][a]
+        const int a = i % GD, b = (i / GD) % GD, cfg = i / (GD * GD);           // s_zt[cfg][b][a] = Z[a][b];  s_zn[cfg][b][a] = Z[b][a]
         const bool ok = a < p.n_gen && b < p.n_gen;
         const double* et = p.zsub + (((long long)cfg * p.z_rows + (ok ? a : 0)) * p.z_cols + (ok ? b : 0)) * 2;
         const double* en = p.zsub + (((long long)cfg * p.z_rows + (ok ? b : 0)) * p.z_cols + (ok ? a : 0)) * 2;
@@ -129,14 +141,14 @@ dps_adjoint_kernel(const BwdParams p) {
     const int ctrl = CTRL ? p.ctrl[g] : 0;
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
-    double2* xch_w = s_xch + warp * 64;
+    double2* xch_w = WIDE ? s_xch : s_xch + warp * 64;
     int buf = 0;
 
     // exchange (a, b) with the other generators of this trajectory; afterwards xb[j] holds generator j's pair
     auto exchange = [&](double a, double b) -> const double2* {
-        double2* cw = xch_w + buf * 32;
+        double2* cw = xch_w + buf * (WIDE ? Cfg::THREADS : 32);
         if (gen_live) cw[lane] = make_double2(a, b);
-        __syncwarp();
+        if (WIDE) __syncthreads(); else __syncwarp();
         buf ^= 1;
         return cw + base;
     };
@@ -154,7 +166,7 @@ dps_adjoint_kernel(const BwdParams p) {
         const double2* xb = exchange(i_re, i_im);
         v_re = 0.0;
         v_im = 0.0;
-        if (!p.z_per_sim) {
+        if (!WIDE && !p.z_per_sim) {
             const double* zr_ = s_ztr + cfg * G * G + gl;
             const double* zi_ = s_zti + cfg * G * G + gl;
 #pragma unroll
@@ -351,7 +363,7 @@ dps_adjoint_kernel(const BwdParams p) {
                     gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
                 }
                 const long long gz_row = (long long)p.z_cols * 2 * P;
-                if (!p.z_per_sim && !ZGRAD) {
+                if (!WIDE && !p.z_per_sim && !ZGRAD) {
                     const double* zr_ = s_znr + cfg * G * G + gl;
                     const double* zi_ = s_zni + cfg * G * G + gl;
 #pragma unroll
@@ -420,7 +432,8 @@ dps_adjoint_kernel(const BwdParams p) {
 }
 
 // Work-queue planning of the adjoint (see plan_work_queue in dps_forward_pair.cuh): chunks are whole checkpoint segments.
-static cudaError_t plan_adjoint_queue(BwdParams& q, const void* kern, int threads, size_t smem, long long groups, unsigned* grid,
+template <class PT>
+static cudaError_t plan_adjoint_queue(PT& q, const void* kern, int threads, size_t smem, long long groups, unsigned* grid,
                                       cudaStream_t stream) {
     q.q_items = 0;
     if (q.q_counter == nullptr || groups > q.q_capacity || groups > 0x3fffffff) return cudaSuccess;
@@ -450,22 +463,23 @@ static cudaError_t plan_adjoint_queue(BwdParams& q, const void* kern, int thread
     return cudaMemsetAsync(q.q_counter, 0, sizeof(int) * (size_t)(groups + 1), stream);
 }
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
-static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
+template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
+static cudaError_t launch_bwd_one(const PT& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
-    const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * G * DPS_N_SLOTS + sizeof(short) * G * DPS_N_SLOTS +
-                        (p.z_per_sim ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
-    auto kern = dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, false>;
+    const int GG = C::WIDE ? p.n_gen : G;
+    const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * GG * DPS_N_SLOTS + sizeof(short) * GG * DPS_N_SLOTS +
+                        ((C::WIDE || p.z_per_sim) ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
+    auto kern = dps_adjoint_kernel<PT, G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long long spb = (long long)C::WARPS * C::SPW;
+    const long long spb = C::WIDE ? C::THREADS / ((p.n_gen + 31) & ~31) : (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + spb - 1) / spb;
     // the work-queue build exists for the common case (no network gradient: those accumulate dL/dZ in HBM across chunks)
     if constexpr (!ZGRAD && FASTPAR) {
-        auto kern_q = dps_adjoint_kernel<G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, true>;
-        BwdParams q = p;
+        auto kern_q = dps_adjoint_kernel<PT, G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, true>;
+        PT q = p;
         unsigned grid = (unsigned)blocks;
         cudaError_t e = plan_adjoint_queue(q, (const void*)kern_q, C::THREADS, smem, blocks, &grid, stream);
         if (e != cudaSuccess) return e;
@@ -482,30 +496,37 @@ static cudaError_t launch_bwd_one(const BwdParams& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int G, bool CTRL, bool ZGRAD, int SOLVER>
-static cudaError_t launch_bwd_ngp(const BwdParams& p, int ngp, cudaStream_t stream) {
+template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER>
+static cudaError_t launch_bwd_ngp(const PT& p, int ngp, cudaStream_t stream) {
     // accumulators for the register slots only (machine constants / set points: the usual identification leaves) or for
     // every slot; the network-gradient variant is only built with all of them (it is the rare one)
     // fast constants whenever the plan allows it and the common accumulator set is enough; the generic reader with all
     // accumulators covers everything else
     if constexpr (!ZGRAD) {
-        if (ngp <= DPS_N_REG_SLOTS && p.fast_par) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS, true>(p, stream);
-        if (p.fast_par) return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, true>(p, stream);
+        if (ngp <= DPS_N_REG_SLOTS && p.fast_par) return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS, true>(p, stream);
+        if (p.fast_par) return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, true>(p, stream);
     }
-    return launch_bwd_one<G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, false>(p, stream);
+    return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, false>(p, stream);
 }
 
-template <int G, bool CTRL, bool ZGRAD>
-static cudaError_t launch_bwd_solver(const BwdParams& p, int ngp, cudaStream_t stream) {
-    if (p.solver == DPS_EULER) return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_EULER>(p, ngp, stream);
-    if (p.solver == DPS_HEUN) return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_HEUN>(p, ngp, stream);
-    return launch_bwd_ngp<G, CTRL, ZGRAD, DPS_RK4>(p, ngp, stream);
+template <class PT, int G, bool CTRL, bool ZGRAD>
+static cudaError_t launch_bwd_solver(const PT& p, int ngp, cudaStream_t stream) {
+    if (p.solver == DPS_EULER) return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_EULER>(p, ngp, stream);
+    if (p.solver == DPS_HEUN) return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_HEUN>(p, ngp, stream);
+    return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_RK4>(p, ngp, stream);
 }
 
 template <int G>
 cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, int ngp, cudaStream_t stream) {
-    if (p.g_zsub != nullptr) return ctrl ? launch_bwd_solver<G, true, true>(p, ngp, stream) : launch_bwd_solver<G, false, true>(p, ngp, stream);
-    return ctrl ? launch_bwd_solver<G, true, false>(p, ngp, stream) : launch_bwd_solver<G, false, false>(p, ngp, stream);
+    if (p.g_zsub != nullptr) return ctrl ? launch_bwd_solver<BwdParams, G, true, true>(p, ngp, stream) : launch_bwd_solver<BwdParams, G, false, true>(p, ngp, stream);
+    return ctrl ? launch_bwd_solver<BwdParams, G, true, false>(p, ngp, stream) : launch_bwd_solver<BwdParams, G, false, false>(p, ngp, stream);
+}
+
+// 17..128 generators (G = 0: run-time generator count)
+inline cudaError_t launch_bwd_wide_impl(const BwdWideParams& p, bool ctrl, int ngp, cudaStream_t stream) {
+    if (p.g_zsub != nullptr || p.z_per_sim) return cudaErrorInvalidValue;
+    return ctrl ? launch_bwd_solver<BwdWideParams, 0, true, false>(p, ngp, stream)
+                : launch_bwd_solver<BwdWideParams, 0, false, false>(p, ngp, stream);
 }
 
 }  // namespace dps

@@ -4,7 +4,10 @@
 
 namespace dps {
 
-struct BwdParams {
+// MAXG = MAX_G for the warp-exchange adjoint (<= 16 generators), MAX_GW for the wide one (17..128 generators: block-wide
+// exchange, tables of ~28 KB -- inside the 32 KB kernel-parameter limit).
+template <int MAXG>
+struct BwdParamsT {
     long long P;
     int n_gen, solver, n_steps;
     double dt, fn;
@@ -22,12 +25,12 @@ struct BwdParams {
     int fast_par;              // plan pmode 1/3: only the DPS_N_REG_SLOTS leading slots may differ per trajectory
     int seg_step[MAX_SEG];
     int seg_cfg[MAX_SEG];
-    int ctrl[MAX_G];
-    unsigned rec_mask[MAX_G];
-    short rec_chan[MAX_G][DPS_N_FIELDS];
+    int ctrl[MAXG];
+    unsigned rec_mask[MAXG];
+    short rec_chan[MAXG][DPS_N_FIELDS];
     short obs_chan[MAX_EXTRA_OBS][2];
-    short slot_vary[MAX_G * DPS_N_SLOTS];
-    short want_row[MAX_G * DPS_N_SLOTS];
+    short slot_vary[MAXG * DPS_N_SLOTS];
+    short want_row[MAXG * DPS_N_SLOTS];
     // Work queue (q_items > 0; same scheme as the forward stepper, dps_internal.h): items = (block group, chunk of
     // q_chunk_ckpts checkpoint segments), chunk 0 = the LAST segments of the run (the sweep walks time backwards).  The
     // co-state and the slot-gradient accumulators of a group travel between its chunks through g_x0 / gslot.
@@ -35,5 +38,7 @@ struct BwdParams {
     int* q_counter;
     int* q_progress;
 };
+using BwdParams = BwdParamsT<MAX_G>;
+using BwdWideParams = BwdParamsT<MAX_GW>;
 
 }  // namespace dps

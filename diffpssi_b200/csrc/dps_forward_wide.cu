@@ -52,6 +52,23 @@ struct WideMmaGeom {
     }
 };
 
+// PMODE 2 reader of the wide stepper: any controller constant may differ per trajectory.  The shared-memory budget is spent
+// on Z, so there is no room for a second table saying which slots vary: a varying slot's entry of the uniform table holds
+// a NaN whose payload is the row of vpar ("NaN boxing"; written once at block start from WideParams::slot_vary).
+constexpr int WIDE_BOX_HI = 0x7FFDEAD0;
+struct ParamWideGen {
+    const double* pm;        // registers, [DPS_N_REG_SLOTS]
+    const double* up;        // shared memory row of this generator: value, or boxed vpar row
+    const double* vpar;
+    long long P, s;
+    __device__ __forceinline__ double operator()(int slot) const {
+        if (slot < DPS_N_REG_SLOTS) return pm[slot];
+        const double u = up[slot];
+        if (__double2hiint(u) == WIDE_BOX_HI) return __ldg(vpar + (long long)__double2loint(u) * P + s);
+        return u;
+    }
+};
+
 template <int CM, int PMODE, int SOLVER, bool MMA>
 __global__ void __launch_bounds__(WIDE_THREADS, 1)
 dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
@@ -105,7 +122,8 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     if (!SPLIT) {
         for (int i = t; i < G * DPS_N_SLOTS; i += blockDim.x) {
             const int gi = i / DPS_N_SLOTS, k = i - gi * DPS_N_SLOTS;
-            s_upar[gi * UPS + k] = p.upar[i];
+            const int vi = (PMODE == 2) ? p.slot_vary[gi][k] : -1;
+            s_upar[gi * UPS + k] = (vi >= 0) ? __hiloint2double(WIDE_BOX_HI, vi) : p.upar[i];
         }
     }
     auto load_z = [&](int cfg) {
@@ -149,6 +167,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
     }
     ParamRegs par_fast{pm, up};
     ParamConst par_const{pm, p.cpar};
+    ParamWideGen par_gen{pm, up, p.vpar, P, s};
 
     double x[NS];
     {
@@ -170,6 +189,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
         dps_sincos(X[DPS_X_DELTA], &sd, &cd);
         double i_re, i_im;
         if (PMODE == 3) injection(X, par_const, sd, cd, i_re, i_im);
+        else if (PMODE == 2) injection(X, par_gen, sd, cd, i_re, i_im);
         else injection(X, par_fast, sd, cd, i_re, i_im);
         double2* cb = s_cur + (buf * SPB + ((sl < SPB) ? sl : SPB - 1)) * GP;
         double v_re, v_im;
@@ -249,6 +269,7 @@ dps_step_wide_kernel(const WideParams p, int WG, int SPB) {
         v_im = via + vib;
         }
         if (PMODE == 3) stage_derivatives<CTRL>(X, par_const, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
+        else if (PMODE == 2) stage_derivatives<CTRL>(X, par_gen, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         else stage_derivatives<CTRL>(X, par_fast, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
         if (last_stage && (rec_mask >> DPS_N_STATES)) {
             const short* ch = p.rec_chan[g];
@@ -387,7 +408,7 @@ cudaError_t launch_forward_wide(const WideParams& p, int cmask, int pmode, cudaS
         if (p.solver == DPS_HEUN) return launch_wide_one<C, M, DPS_HEUN>(p, stream, regs, threads, sims_per_block);   \
         return launch_wide_one<C, M, DPS_RK4>(p, stream, regs, threads, sims_per_block);                       \
     }
-    DPS_WCASE(0, 1) DPS_WCASE(7, 1) DPS_WCASE(7, 3) DPS_WCASE(-1, 1)
+    DPS_WCASE(0, 1) DPS_WCASE(7, 1) DPS_WCASE(7, 3) DPS_WCASE(-1, 1) DPS_WCASE(0, 2) DPS_WCASE(7, 2) DPS_WCASE(-1, 2)
 #undef DPS_WCASE
     return cudaErrorInvalidValue;
 }

@@ -85,6 +85,7 @@ struct WideParams {
     short rec_chan[MAX_GW][DPS_N_FIELDS];
     short obs_chan[MAX_EXTRA_OBS][2];
     short reg_vary[MAX_GW][DPS_N_REG_SLOTS];   // row of vpar or -1, leading (register) slots only
+    short slot_vary[MAX_GW][DPS_N_SLOTS];      // PMODE 2: row of vpar or -1 for every slot (read once, at block start)
     double cpar[DPS_N_SLOTS];
 };
 

@@ -502,6 +502,57 @@ def optimizer_cases(sel):
         print('wrote', name, 'losses', np.stack(losses).min(axis=1))
 
 
+def wide_grad_case(sel):
+    """Gradients on a system with more than 16 generators (the wide stepper / wide adjoint): tiled grid with 20 cells
+    (100 buses, 20 machines with SEXS+TGOV1+STAB1), RK4, machine and controller leaves on several machines; reference
+    autograd, FD-checked on the first leaf."""
+    import torch
+    from diffpssi_b200 import grids
+    name = 'grad_tiled20_rk4'
+    if sel and not any(s in name for s in sel):
+        return
+    rng = np.random.RandomState(17)
+    P, T = 3, 160
+    grid = grids.tiled(20)
+    ov = {('gen', 'M3', 'h'): 6.175 * rng.uniform(0.8, 1.25, P),
+          ('gen', 'M7', 'x_d_t'): 0.3 * rng.uniform(0.8, 1.25, P),
+          ('gen', 'M12', 'd'): rng.uniform(0.5, 2.0, P),
+          ('gen', 'M18', 'exciter.pt1_lim.gain_pt1'): 100.0 * rng.uniform(0.8, 1.25, P),
+          ('gen', 'M0', 'governor.lead_lag.t_1'): 1.0 * rng.uniform(0.8, 1.25, P)}
+    events = [(0.1, 0.15, 'A3')]
+    chans = ['M%d.omega' % c for c in (0, 3, 7, 12, 18)] + ['M3.e_q_st']
+
+    def run(ovv, grad):
+        sim, leaves = rh.build(grid, P, 'rk4', DT, T * DT, events, ovv, requires_grad=grad)
+        t, rec, names, snap, rec_t = rh.run_full(sim)
+        idx = [names.index(c) for c in chans]
+        return leaves, rec_t[:, :, idx], names, snap, t, rec
+
+    leaves, out, names, snap, t, rec = run(ov, True)
+    tt = torch.tensor(t)[None, :, None]
+    target = 0.002 * torch.sin(2.0 * tt) * torch.ones_like(out.real)
+    loss = ((out.real - target) ** 2).mean(dim=(1, 2))
+    loss.sum().backward()
+    extra = {'override/' + '|'.join(k): v for k, v in ov.items()}
+    extra.update({'grad/' + '|'.join(k): v.grad.real.numpy().reshape(-1).copy() for k, v in leaves.items()})
+    extra['loss'] = loss.detach().numpy()
+    extra['loss_channels'] = np.array(chans)
+    extra['target'] = target[0, :, 0].numpy()
+    k0 = list(ov.keys())[0]
+    h = 1e-6 * np.abs(ov[k0]).max()
+    lp = []
+    for sgn in (+1, -1):
+        ov2 = dict(ov)
+        ov2[k0] = ov[k0] + sgn * h
+        _, o2, _, _, _, _ = run(ov2, False)
+        lp.append(((o2.real - target) ** 2).mean(dim=(1, 2)).numpy())
+    fd = (lp[0] - lp[1]) / (2 * h)
+    g = extra['grad/' + '|'.join(k0)]
+    print('   FD check on %s: max rel diff %.2e' % ('|'.join(k0), np.abs(fd - g).max() / np.abs(g).max()))
+    keep = [i for i, n in enumerate(names) if not n.startswith('bus:')]
+    save_case(name, t, rec[:, :, keep], [names[i] for i in keep], snap, events, 'rk4', extra, stride=20)
+
+
 def main():
     sel = sys.argv[1:]
     os.makedirs(os.path.join(GOLD, 'grids'), exist_ok=True)
@@ -519,6 +570,7 @@ def main():
     headline_cases(sel)
     ident_range_grad_case(sel)
     optimizer_cases(sel)
+    wide_grad_case(sel)
 
 
 if __name__ == '__main__':

@@ -45,8 +45,7 @@ def test_plan_validation_errors_are_reported():
                          z_cols=200))
     with pytest.raises(engine.EngineError, match='shared by the batch'):
         engine.Plan(dict(wide, z_per_sim=1))
-    with pytest.raises(engine.EngineError, match='adjoint is not available'):
-        engine.Plan(dict(wide, ckpt_stride=8))
+    assert engine.Plan(dict(wide, ckpt_stride=8)).n_checkpoints() == 1        # the wide stepper has an adjoint since round 2
     with pytest.raises(engine.EngineError, match='n_cfg'):
         engine.Plan(dict(topo, step_cfg=[0, 3, 0, 0]))
     ck = engine.Plan(dict(topo, ckpt_stride=3))

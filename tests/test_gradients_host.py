@@ -13,7 +13,9 @@ CASES = [('grad_ibb_heun', 'ibb'), ('grad_ibb_euler', 'ibb'), ('grad_ibb_rk4', '
          ('grad_ibb_z_heun', 'ibb'), ('grad_k2a_z_heun', 'k2a'),
          # BASELINE config 4 as the reference runs it: H / D / X_d' leaves from the 0.5x..2x identification range, the full
          # 10 s, loss = per-sim MSE against the reference's own golden trajectory (ibb_model.npy)
-         ('grad_ibb_range_heun', 'ibb')]
+         ('grad_ibb_range_heun', 'ibb'),
+         # more than 16 generators (tiled grid, 20 machines with all controllers, RK4): wide stepper + wide adjoint
+         ('grad_tiled20_rk4', 'tiled20')]
 
 
 def loss_of(result, gold, names):
