@@ -77,7 +77,7 @@ __device__ __forceinline__ void stage_vjp(const double* x, const PR& par, int ct
             v_pss = clampd(o2, -par(DPS_S_S_HLIM), par(DPS_S_S_HLIM));
         }
         if (has_avr) {
-            v_abs = sqrt(v_re * v_re + v_im * v_im);
+            v_abs = dps_sqrt(v_re * v_re + v_im * v_im);
             const double sig = has_pss ? (v_abs - v_pss) : v_abs;
             u_a = (par(DPS_S_A_VSET) - sig) + par(DPS_S_A_BIAS);
             o_a = par(DPS_S_A_R) * u_a + par(DPS_S_A_OMR) * x[DPS_X_AVR_LL];
@@ -90,7 +90,7 @@ __device__ __forceinline__ void stage_vjp(const double* x, const PR& par, int ct
             p_m = o_g - par(DPS_S_G_DT) * omega;
         }
     }
-    const double inv1w = 1.0 / (1.0 + omega);
+    const double inv1w = dps_rcp(1.0 + omega);
     const double t_m = p_m * inv1w;
 
     // ---- machine equations, synchronous_machine.py:158-164 -----------------------------------------------------------
@@ -211,8 +211,9 @@ __device__ __forceinline__ void stage_vjp(const double* x, const PR& par, int ct
         const double d_sig = -d_u;
         if (has_pss) d_vpss = -d_sig;                                   // sig = |v| - v_pss
         if (v_abs > 0.0) {
-            dv_re += d_sig * (v_re / v_abs);
-            dv_im += d_sig * (v_im / v_abs);
+            const double t = d_sig * dps_rcp(v_abs);
+            dv_re += t * v_re;
+            dv_im += t * v_im;
         }
     } else {
         gp[DPS_S_EFD0] += d_efd;

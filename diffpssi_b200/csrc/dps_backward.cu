@@ -28,14 +28,14 @@
 namespace dps {
 
 template <int G>
-cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, int ngp, cudaStream_t stream);
-#define DPS_EXTERN(G) extern template cudaError_t launch_bwd_g<G>(const BwdParams&, bool, int, cudaStream_t);
+cudaError_t launch_bwd_g(const BwdParams& p, int cmask, int ngp, cudaStream_t stream);
+#define DPS_EXTERN(G) extern template cudaError_t launch_bwd_g<G>(const BwdParams&, int, int, cudaStream_t);
 DPS_EXTERN(1) DPS_EXTERN(2) DPS_EXTERN(3) DPS_EXTERN(4) DPS_EXTERN(5) DPS_EXTERN(6) DPS_EXTERN(8) DPS_EXTERN(10) DPS_EXTERN(16)
 #undef DPS_EXTERN
 
-cudaError_t launch_bwd_wide(const BwdWideParams& p, bool ctrl, int ngp, cudaStream_t stream);
+cudaError_t launch_bwd_wide(const BwdWideParams& p, int cmask, int ngp, cudaStream_t stream);
 
-static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl, int ngp, cudaStream_t stream) {
+static cudaError_t launch_backward(const BwdParams& p, int g_template, int ctrl, int ngp, cudaStream_t stream) {
 #ifdef DPS_ONLY_G10      // kernel A/B experiment builds (tools/build_variant.sh)
     return g_template == 10 ? launch_bwd_g<10>(p, ctrl, ngp, stream) : cudaErrorInvalidValue;
 #endif
@@ -57,8 +57,13 @@ static cudaError_t launch_backward(const BwdParams& p, int g_template, bool ctrl
 
 using namespace dps;
 
+// Segment scratch of the adjoint: per step of a checkpoint segment and per stage of the scheme, the stage input (13 states,
+// 6 for bare machines), sin/cos of the rotor angle and the bus voltage of every generator (dps_backward.cuh).
 static size_t adjoint_scratch_bytes(const dps_plan* plan, int64_t P) {
-    return sizeof(double) * (size_t)plan->topo.ckpt_stride * plan->topo.n_gen * DPS_N_STATES * (size_t)P;
+    const int solver = plan->topo.solver;
+    const size_t stages = (solver == DPS_EULER) ? 1 : (solver == DPS_HEUN ? 2 : 4);
+    const size_t rows = stages * (((plan->any_ctrl ? DPS_N_STATES : 6) + 5) & ~(size_t)1);
+    return sizeof(double) * (size_t)plan->topo.ckpt_stride * plan->topo.n_gen * rows * (size_t)P;
 }
 
 // 17..128 generators: same sweep, tables sized for MAX_GW, block-wide exchange (dps_backward_wide.cu)
@@ -74,10 +79,10 @@ static int backward_wide(const dps_plan* plan, int64_t P, const double* upar, co
     p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = nullptr; p.scratch = (double*)workspace;
     p.q_counter = (int*)((char*)workspace + adjoint_scratch_bytes(plan, P));
     p.q_progress = p.q_counter + 1;
-    p.q_capacity = (int)(P / 8 + 64);
+    p.q_capacity = (int)(P / 2 + 64);
     p.n_obs = w.n_obs; p.z_rows = w.z_rows; p.z_cols = w.z_cols; p.n_cfg = w.n_cfg; p.z_per_sim = 0;
     p.ckpt_stride = w.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
-    p.fast_par = (plan->pmode != 2) ? 1 : 0;
+    p.pmode = plan->pmode;
     p.n_seg = (int)plan->seg_step.size();
     for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[i]; p.seg_cfg[i] = plan->seg_cfg[i]; }
     for (int g = 0; g < G; ++g) {
@@ -87,6 +92,8 @@ static int backward_wide(const dps_plan* plan, int64_t P, const double* upar, co
         for (int k = 0; k < DPS_N_SLOTS; ++k) p.slot_vary[g * DPS_N_SLOTS + k] = w.slot_vary[g][k];
     }
     memcpy(p.obs_chan, w.obs_chan, sizeof(p.obs_chan));
+    p.rec_uniform = 1;
+    for (int g = 1; g < G; ++g) p.rec_uniform &= (p.rec_mask[g] == p.rec_mask[0]) ? 1 : 0;
     int n_want = 0;
     for (int i = 0; i < MAX_GW * DPS_N_SLOTS; ++i) p.want_row[i] = -1;
     for (int i = 0; i < G * DPS_N_SLOTS; ++i)
@@ -104,7 +111,7 @@ static int backward_wide(const dps_plan* plan, int64_t P, const double* upar, co
     for (int g = 0; g < G; ++g)
         for (int k = 0; k < DPS_N_SLOTS; ++k)
             if (want[g * DPS_N_SLOTS + k] && k + 1 > ngp) ngp = k + 1;
-    cudaError_t e = launch_bwd_wide(p, plan->any_ctrl, ngp, (cudaStream_t)stream);
+    cudaError_t e = launch_bwd_wide(p, plan->cmask, ngp, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("dps_backward: launch failed: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }
@@ -114,8 +121,8 @@ extern "C" {
 size_t dps_workspace_bytes(const dps_plan* plan, int64_t P) {
     if (!plan || plan->topo.ckpt_stride <= 0 || P < 1) return 0;
     // per-step state scratch of one checkpoint segment + the work-queue words (one dequeue counter, one progress word per
-    // block group; a group holds at least 8 trajectories)
-    return adjoint_scratch_bytes(plan, P) + sizeof(int) * (size_t)(P / 8 + 66);
+    // block group; a group holds at least 2 trajectories)
+    return adjoint_scratch_bytes(plan, P) + sizeof(int) * (size_t)(P / 2 + 66);
 }
 
 int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const double* vpar, const double* zsub,
@@ -143,16 +150,18 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     p.g_x0 = g_x0; p.gslot = gslot; p.g_zsub = g_zsub; p.scratch = (double*)workspace;
     p.q_counter = (int*)((char*)workspace + adjoint_scratch_bytes(plan, P));
     p.q_progress = p.q_counter + 1;
-    p.q_capacity = (int)(P / 8 + 64);
+    p.q_capacity = (int)(P / 2 + 64);
     p.n_obs = b.n_obs; p.z_rows = b.z_rows; p.z_cols = b.z_cols; p.n_cfg = b.n_cfg; p.z_per_sim = b.z_per_sim;
     p.ckpt_stride = b.ckpt_stride; p.n_ckpt = (int)dps_n_checkpoints(plan);
-    p.fast_par = (plan->pmode != 2) ? 1 : 0;
+    p.pmode = plan->pmode;
     p.n_seg = (int)plan->seg_step.size();
     for (int i = 0; i < p.n_seg; ++i) { p.seg_step[i] = plan->seg_step[i]; p.seg_cfg[i] = plan->seg_cfg[i]; }
     memcpy(p.ctrl, b.ctrl, sizeof(p.ctrl));
     memcpy(p.rec_mask, b.rec_mask, sizeof(p.rec_mask));
     memcpy(p.rec_chan, b.rec_chan, sizeof(p.rec_chan));
     memcpy(p.obs_chan, b.obs_chan, sizeof(p.obs_chan));
+    p.rec_uniform = 1;
+    for (int g = 1; g < b.n_gen; ++g) p.rec_uniform &= (p.rec_mask[g] == p.rec_mask[0]) ? 1 : 0;
     memcpy(p.slot_vary, b.slot_vary, sizeof(p.slot_vary));
     int n_want = 0;
     for (int i = 0; i < MAX_G * DPS_N_SLOTS; ++i) p.want_row[i] = -1;
@@ -173,7 +182,7 @@ int dps_backward(const dps_plan* plan, int64_t P, const double* upar, const doub
     for (int g = 0; g < b.n_gen; ++g)
         for (int k = 0; k < DPS_N_SLOTS; ++k)
             if (want[g * DPS_N_SLOTS + k] && k + 1 > ngp) ngp = k + 1;
-    cudaError_t e = launch_backward(p, plan->g_template, plan->any_ctrl, ngp, (cudaStream_t)stream);
+    cudaError_t e = launch_backward(p, plan->g_template, plan->cmask, ngp, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("dps_backward: launch failed: %s", cudaGetErrorString(e)); return 3; }
     return 0;
 }

@@ -19,11 +19,24 @@ namespace dps {
 // of a 256-thread block, currents and voltage cotangents are exchanged through block-wide shared-memory lines behind
 // __syncthreads, and Z is read from global memory (L2-resident: 160 KB for 100 generators).  Same per-thread arithmetic
 // (dps_adjoint.cuh), same checkpoint / scratch layout, so the forward wide stepper's checkpoints feed it directly.
+#ifndef DPS_BWD_AOS
+#define DPS_BWD_AOS 0              // segment scratch: 1 = one contiguous record per thread, 0 = row-major [row][trajectory][generator]
+#endif
+#ifndef DPS_BWD_L1PF
+#define DPS_BWD_L1PF 1             // prefetch the next scratch block towards L1 while a stage is transposed
+#endif
+#ifndef DPS_BWD_WARPS
+#define DPS_BWD_WARPS 4            // warps per block of the (<= 16 generator) adjoint
+#endif
+#ifndef DPS_BWD_MIN_BLOCKS
+#define DPS_BWD_MIN_BLOCKS 2       // resident 128-thread blocks per SM the register allocation aims at (A/B: tools/build_variant.sh)
+#endif
+
 template <int G>
 struct BwdCfg {
     static constexpr bool WIDE = (G == 0);
     static constexpr int SPW = WIDE ? 0 : 32 / (G ? G : 1);       // trajectories per warp
-    static constexpr int WARPS = WIDE ? 8 : 4;
+    static constexpr int WARPS = WIDE ? 8 : DPS_BWD_WARPS;
     static constexpr int THREADS = 32 * WARPS;
 };
 
@@ -39,19 +52,23 @@ struct SlotGrads {
     __device__ __forceinline__ double& operator[](int k) { return (k < N) ? v[k < N ? k : 0] : dummy; }
 };
 
-template <bool FAST>
-struct ReaderPick {
-    __device__ __forceinline__ static const ParamRegs& get(const ParamRegs& a, const ParamReader<true>&) { return a; }
-};
-template <>
-struct ReaderPick<false> {
-    __device__ __forceinline__ static const ParamReader<true>& get(const ParamRegs&, const ParamReader<true>& b) { return b; }
-};
-
-template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR, bool QUEUED = false>
-__global__ void __launch_bounds__(BwdCfg<G>::THREADS, BwdCfg<G>::WIDE ? 1 : 2)
+// CM: controller set of the generators -- 0 none (bare machines), 7 all three on every generator (compile time: the
+// has_avr / has_gov / has_pss tests of the stage code fold away and the transposed stage is one straight-line block),
+// -1 mixed (read per generator).  PM: how constants are read -- 0 any slot may differ per trajectory (vary table), 1 the
+// DPS_N_REG_SLOTS leading slots in registers + uniform controller constants from shared memory.
+// INREG (ckpt_stride 1 only: the forward pass kept the state before EVERY step): nothing is re-integrated and there is no
+// scratch; the sweep evaluates the stages of a step in registers from the checkpoint.  Wins for small systems (bare
+// machines: a stage evaluation is cheaper than the round trip of its record through L2).
+template <class PT, int G, int CM, bool ZGRAD, int SOLVER, int NGP, int PM, bool QUEUED = false, bool INREG = false>
+#ifdef DPS_BWD_MAXNREG
+__global__ void __maxnreg__(DPS_BWD_MAXNREG)
+#else
+__global__ void __launch_bounds__(BwdCfg<G>::THREADS, BwdCfg<G>::WIDE ? 1 : DPS_BWD_MIN_BLOCKS)
+#endif
 dps_adjoint_kernel(const PT p) {
     using Cfg = BwdCfg<G>;
+    constexpr bool CTRL = (CM != 0);
+    constexpr bool FASTPAR = (PM != 0);
     constexpr bool WIDE = Cfg::WIDE;
     constexpr int SPW = Cfg::SPW;
     const int GG = WIDE ? p.n_gen : G;                            // generators (table strides)
@@ -137,8 +154,12 @@ dps_adjoint_kernel(const PT p) {
         for (int k = 0; k < DPS_N_REG_SLOTS; ++k) pm[FASTPAR ? k : 0] = par_gen(k);
     }
     const ParamRegs par_fast{pm, s_upar + g * DPS_N_SLOTS};
-    const auto& par = ReaderPick<FASTPAR>::get(par_fast, par_gen);
-    const int ctrl = CTRL ? p.ctrl[g] : 0;
+    auto pick_reader = [&]() -> decltype(auto) {
+        if constexpr (PM == 1) return (par_fast);
+        else return (par_gen);
+    };
+    const auto& par = pick_reader();
+    const int ctrl = (CM > 0) ? CM : (CM < 0 ? p.ctrl[g] : 0);
     const long long zb = p.z_per_sim ? P : 1;
     const long long zs = p.z_per_sim ? s : 0;
     double2* xch_w = WIDE ? s_xch : s_xch + warp * 64;
@@ -187,14 +208,20 @@ dps_adjoint_kernel(const PT p) {
         }
         stage_derivatives<CTRL>(X, par, ctrl, p.fn, sd, cd, v_re, v_im, f, alg);
     };
-    auto cfg_of = [&](int step) {
+    // index of the fault-configuration segment that contains `step` (searched once per checkpoint segment; the step loops
+    // below move it incrementally)
+    auto seg_of = [&](int step) {
         int seg = 0;
         while (seg + 1 < p.n_seg && p.seg_step[seg + 1] <= step) ++seg;
-        return p.seg_cfg[seg];
+        return seg;
     };
 
     // the scheme is a template parameter: the stage loops unroll and X[i], sds[i], ... are registers, not a local array
     constexpr int n_stages = (SOLVER == DPS_EULER) ? 1 : (SOLVER == DPS_HEUN ? 2 : 4);
+    // segment scratch: per (step, trajectory, generator) one record of n_stages blocks of SST doubles -- the stage input
+    // (NS states), sin/cos of the rotor angle, the bus voltage, padded to an even count for 128-bit accesses
+    constexpr int SST = (NS + 5) & ~1;
+    constexpr int SROW = n_stages * SST;
     const double dt = p.dt;
     // c_i, b_i of the explicit scheme (Euler b=[1]; Heun c=[0,1], b=[1/2,1/2]; RK4 c=[0,1/2,1/2,1], b=[1/6,1/3,1/3,1/6])
     constexpr double cst[4] = {0.0, (SOLVER == DPS_HEUN) ? 1.0 : 0.5, 0.5, 1.0};
@@ -220,6 +247,8 @@ dps_adjoint_kernel(const PT p) {
     gp.dummy = 0.0;
 
     const unsigned rec_mask = p.rec_mask[g];
+    const bool rec_uniform = p.rec_uniform != 0;                 // every generator records the same set of states
+    const unsigned rec_mask_u = p.rec_mask[0] & 0x1FFFu;
     const short* ch = p.rec_chan[g];
     const long long cs = (long long)p.n_steps * P;
     const int C = p.ckpt_stride;
@@ -229,105 +258,141 @@ dps_adjoint_kernel(const PT p) {
     for (int ck = ck_hi - 1; ck >= ck_lo; --ck) {
         const int k0 = ck * C;
         const int k1 = (k0 + C < p.n_steps) ? (k0 + C) : p.n_steps;
-        // ---- re-integrate the segment, keeping the state at the start of every step ----------------------------------
-        // (ckpt_stride 1: the forward pass stored the state before EVERY step -- nothing to re-integrate, no scratch; the
-        // sweep reads the checkpoints directly.  A quarter of the adjoint's arithmetic and its HBM round trip go away, for
-        // n_steps x n_gen x 13 x P x 8 bytes of checkpoints, which Pss chooses when that fits comfortably.)
-        if (C > 1) {
-            double x[NS], xs[NS], acc[NS], f[NSG];
+        // ---- re-integrate the segment ---------------------------------------------------------------------------------
+        // Everything the transposed stages need -- the stage inputs X_i, sin/cos of the rotor angle and the bus voltage of
+        // every stage -- goes to the scratch here, so that the sweep below evaluates no stage a second time (until round 2
+        // it kept only the step's start state and re-evaluated every stage incl. the network product).  Scratch layout
+        // [step][trajectory][generator][SROW]: a thread's record is contiguous (128-bit stores / loads at immediate
+        // offsets, one running pointer), a warp's records are adjacent.
+        const long long sstep = P * (long long)p.n_gen * SROW;                           // one step further
+#if DPS_BWD_AOS
+        double* const sbase = p.scratch + (s * p.n_gen + g) * SROW;
+#else
+        const long long srow_stride = P * (long long)p.n_gen;                            // one row further
+        double* const sbase = p.scratch + (s * p.n_gen + g);
+#endif
+        int seg = seg_of(k0);
+        int cfg = p.seg_cfg[seg];
+        if constexpr (!INREG) {
+            double xs[NS], xt[NS], acc[NS], f[NSG];
             const double* src = p.ckpt + (((long long)ck * p.n_gen + g) * NSG) * P + s;
 #pragma unroll
-            for (int k = 0; k < NS; ++k) x[k] = src[(long long)k * P];
-            for (int step = k0; step < k1; ++step) {
-                if (live) {
-                    // scratch layout [step][state][trajectory][generator]: the lanes of a warp (consecutive generators of
-                    // consecutive trajectories) touch one contiguous line per state
-                    double* dst = p.scratch + (((long long)(step - k0) * NS) * P + s) * p.n_gen + g;
-                    const long long ks = P * p.n_gen;
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) dst[k * ks] = x[k];
+            for (int k = 0; k < NS; ++k) xs[k] = src[(long long)k * P];
+            int next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
+            double* dst = sbase;
+            for (int step = k0; step < k1; ++step, dst += sstep) {
+                if (step == next_change) {
+                    ++seg;
+                    cfg = p.seg_cfg[seg];
+                    next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
                 }
-                if (step == k1 - 1) break;
-                const int cfg = cfg_of(step);
-#pragma unroll
-                for (int k = 0; k < NS; ++k) xs[k] = x[k];
 #pragma unroll
                 for (int st = 0; st < n_stages; ++st) {
+                    const double* X = (st == 0) ? xs : xt;
                     double sd, cd, v_re, v_im;
                     Algebraics alg;
-                    eval_stage(x, cfg, sd, cd, v_re, v_im, f, alg);
+                    eval_stage(X, cfg, sd, cd, v_re, v_im, f, alg);
+                    if (live) {
+                        double rec[SST];
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) rec[k] = X[k];
+                        rec[NS] = sd; rec[NS + 1] = cd; rec[NS + 2] = v_re; rec[NS + 3] = v_im;
+                        if (SST > NS + 4) rec[SST - 1] = 0.0;
+#if DPS_BWD_AOS
+                        double2* d2 = reinterpret_cast<double2*>(dst + st * SST);
+#pragma unroll
+                        for (int k = 0; k < SST / 2; ++k) d2[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+#else
+                        double* d = dst + (long long)(st * SST) * srow_stride;
+#pragma unroll
+                        for (int k = 0; k < NS + 4; ++k) d[k * srow_stride] = rec[k];
+#endif
+                    }
                     if (SOLVER == DPS_EULER) {
 #pragma unroll
-                        for (int k = 0; k < NS; ++k) x[k] = xs[k] + f[k] * dt;
+                        for (int k = 0; k < NS; ++k) xs[k] = xs[k] + f[k] * dt;
                     } else if (SOLVER == DPS_HEUN) {
                         if (st == 0) {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; x[k] = xs[k] + f[k] * dt; }
+                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; xt[k] = xs[k] + f[k] * dt; }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + ((acc[k] + f[k]) * 0.5) * dt;
+                            for (int k = 0; k < NS; ++k) xs[k] = xs[k] + ((acc[k] + f[k]) * 0.5) * dt;
                         }
                     } else {
                         if (st == 0) {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; x[k] = xs[k] + (f[k] * dt) * 0.5; }
+                            for (int k = 0; k < NS; ++k) { acc[k] = f[k]; xt[k] = xs[k] + (f[k] * dt) * 0.5; }
                         } else if (st == 1) {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; x[k] = xs[k] + (f[k] * dt) * 0.5; }
+                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; xt[k] = xs[k] + (f[k] * dt) * 0.5; }
                         } else if (st == 2) {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; x[k] = xs[k] + f[k] * dt; }
+                            for (int k = 0; k < NS; ++k) { acc[k] = acc[k] + 2.0 * f[k]; xt[k] = xs[k] + f[k] * dt; }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < NS; ++k) x[k] = xs[k] + dps_div6((acc[k] + f[k]) * dt);
+                            for (int k = 0; k < NS; ++k) xs[k] = xs[k] + dps_div6((acc[k] + f[k]) * dt);
                         }
                     }
                 }
             }
         }
         // ---- backward sweep over the segment --------------------------------------------------------------------------
-        for (int step = k1 - 1; step >= k0; --step) {
-            const int cfg = cfg_of(step);
-            double X[4][NS], sds[4], cds[4], vres[4], vims[4];
-            if (C > 1) {
-                const double* src = p.scratch + (((long long)(step - k0) * NS) * P + s) * p.n_gen + g;
-                const long long ks = P * p.n_gen;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) X[0][k] = src[k * ks];
-            } else {
-                const double* src = p.ckpt + (((long long)step * p.n_gen + g) * NSG) * P + s;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) X[0][k] = __ldcs(src + (long long)k * P);      // read once: streaming
-                // the state of the step the sweep visits next is fetched now and consumed a whole step later
-                if (step > 0) {
-                    const double* nxt = src - (long long)p.n_gen * NSG * P;
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (long long)k * P));
-                }
+        // (seg / cfg are those of step k1 - 1, where the re-integration stopped)
+        int seg_lo = p.seg_step[seg];
+        const double* srec = sbase + (long long)(k1 - 1 - k0) * sstep;
+        for (int step = k1 - 1; step >= k0; --step, srec -= sstep) {
+            if (step < seg_lo) {
+                --seg;
+                cfg = p.seg_cfg[seg];
+                seg_lo = p.seg_step[seg];
             }
-            // recorded post-step states: rec[.., step] = x_{step+1}
-            if (live && rec_mask) {
-                const double* gr = p.grad_rec + (long long)step * P + sim;
+            // recorded post-step states: rec[.., step] = x_{step+1}.  Every generator records the same fields in all the
+            // usual cases: the field tests are then uniform branches (no divergence bookkeeping); dead lanes read a valid
+            // (clamped) address and their co-state is never stored.
+            if (rec_uniform) {
+                const double* gr = p.grad_rec + (long long)step * P + s;
 #pragma unroll
                 for (int k = 0; k < NS; ++k)
-                    if (rec_mask & (1u << k)) {
+                    if (rec_mask_u & (1u << k)) {
                         const double* e = gr + ch[k] * cs;
                         lam[k] += *e;
                         // the sweep walks the steps backwards: fetch the previous step's cotangent now, it is consumed
                         // a whole step later (this load sat on the critical path with full HBM latency)
                         if (step > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(e - P));
                     }
+            } else if (live && rec_mask) {
+                const double* gr = p.grad_rec + (long long)step * P + sim;
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (rec_mask & (1u << k)) {
+                        const double* e = gr + ch[k] * cs;
+                        lam[k] += *e;
+                        if (step > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(e - P));
+                    }
             }
-            // stage inputs and their voltages
+            // ckpt_stride 1: the stage inputs and their voltages are evaluated here, from the state the forward pass kept
+            double XR[INREG ? 4 : 1][NS], sds[4], cds[4], vres[4], vims[4];
+            if constexpr (INREG) {
+                const double* src = p.ckpt + (((long long)step * p.n_gen + g) * NSG) * P + s;
 #pragma unroll
-            for (int i = 0; i < n_stages; ++i) {
-                double f[NSG];
-                Algebraics alg;
-                eval_stage(X[i], cfg, sds[i], cds[i], vres[i], vims[i], f, alg);
-                if (i + 1 < n_stages) {
-                    const double ci = cst[i + 1];
+                for (int k = 0; k < NS; ++k) XR[0][k] = __ldcs(src + (long long)k * P);      // read once: streaming
+                // the state of the step the sweep visits next is fetched now and consumed a whole step later
+                if (step > 0) {
+                    const double* nxt = src - (long long)p.n_gen * NSG * P;
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) X[i + 1][k] = X[0][k] + ci * (f[k] * dt);
+                    for (int k = 0; k < NS; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (long long)k * P));
+                }
+#pragma unroll
+                for (int i = 0; i < n_stages; ++i) {
+                    double f[NSG];
+                    Algebraics alg;
+                    eval_stage(XR[INREG ? i : 0], cfg, sds[i], cds[i], vres[i], vims[i], f, alg);
+                    if (i + 1 < n_stages) {
+                        const double ci = cst[i + 1];
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) XR[INREG ? i + 1 : 0][k] = XR[0][k] + ci * (f[k] * dt);
+                    }
                 }
             }
             // transposed stages, last to first
@@ -349,8 +414,41 @@ dps_adjoint_kernel(const PT p) {
                     for (int k = 0; k < 7; ++k)
                         if (rec_mask & (1u << (NSG + k))) *av[k] = gr[ch[NSG + k] * cs];
                 }
+                // this stage's forward quantities, from the segment scratch; the block the sweep needs next (the previous
+                // stage, or the last stage of the previous step) is pulled towards the SM meanwhile
+                double Xi[NS], sdi, cdi, vri, vii;
+                if constexpr (INREG) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) Xi[k] = XR[INREG ? i : 0][k];
+                    sdi = sds[i]; cdi = cds[i]; vri = vres[i]; vii = vims[i];
+                } else {
+                    double rec[SST];
+#if DPS_BWD_AOS
+                    const double2* d2 = reinterpret_cast<const double2*>(srec + i * SST);
+#pragma unroll
+                    for (int k = 0; k < SST / 2; ++k) {
+                        const double2 v = d2[k];
+                        rec[2 * k] = v.x;
+                        rec[2 * k + 1] = v.y;
+                    }
+#else
+                    const double* d = srec + (long long)(i * SST) * srow_stride;
+#pragma unroll
+                    for (int k = 0; k < NS + 4; ++k) rec[k] = d[k * srow_stride];
+#endif
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) Xi[k] = rec[k];
+                    sdi = rec[NS]; cdi = rec[NS + 1]; vri = rec[NS + 2]; vii = rec[NS + 3];
+#if DPS_BWD_AOS && DPS_BWD_L1PF
+                    const double* nxt = (i > 0) ? srec + (i - 1) * SST : srec - sstep + (n_stages - 1) * SST;
+                    if (i > 0 || step > k0) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 16));
+                    }
+#endif
+                }
                 double dsd, dcd, dv_re, dv_im;
-                stage_vjp<CTRL>(X[i], par, ctrl, p.fn, sds[i], cds[i], vres[i], vims[i], dk, ac, dx, gp, dsd, dcd, dv_re, dv_im);
+                stage_vjp<CTRL>(Xi, par, ctrl, p.fn, sdi, cdi, vri, vii, dk, ac, dx, gp, dsd, dcd, dv_re, dv_im);
                 // dI = Z^T dV over the generator rows ...
                 const double2* xb = exchange(dv_re, dv_im);
                 double di_re = 0.0, di_im = 0.0;
@@ -359,7 +457,7 @@ dps_adjoint_kernel(const PT p) {
                 double own_re = 0.0, own_im = 0.0;
                 double* gz = nullptr;
                 if (ZGRAD) {
-                    injection(X[i], par, sds[i], cds[i], own_re, own_im);
+                    injection(Xi, par, sdi, cdi, own_re, own_im);
                     gz = p.g_zsub + ((((long long)cfg * p.z_rows) * p.z_cols + g) * 2) * P + s;
                 }
                 const long long gz_row = (long long)p.z_cols * 2 * P;
@@ -402,8 +500,8 @@ dps_adjoint_kernel(const PT p) {
                         }
                     }
                 }
-                injection_vjp(X[i], par, sds[i], cds[i], di_re, di_im, dx, gp, dsd, dcd);
-                dx[DPS_X_DELTA] += dsd * cds[i] - dcd * sds[i];
+                injection_vjp(Xi, par, sdi, cdi, di_re, di_im, dx, gp, dsd, dcd);
+                dx[DPS_X_DELTA] += dsd * cdi - dcd * sdi;
 #pragma unroll
                 for (int k = 0; k < NS; ++k) { dxn[k] = dx[k]; sum_dx[k] += dx[k]; }
             }
@@ -435,11 +533,14 @@ dps_adjoint_kernel(const PT p) {
 template <class PT>
 static cudaError_t plan_adjoint_queue(PT& q, const void* kern, int threads, size_t smem, long long groups, unsigned* grid,
                                       cudaStream_t stream) {
-    q.q_items = 0;
-    if (q.q_counter == nullptr || groups > q.q_capacity || groups > 0x3fffffff) return cudaSuccess;
+    // default: one chunk per block group (a plain launch, blocks numbered by ticket)
+    q.q_items = (int)groups;
+    q.q_groups = (int)groups;
+    q.q_chunk_ckpts = q.n_ckpt;
+    *grid = (unsigned)groups;
+    if (q.q_counter == nullptr || groups > q.q_capacity || groups > 0x3fffffff) return cudaErrorInvalidValue;
     const char* env = getenv("DPS_QUEUE_ROUNDS");
     const int rounds = env ? atoi(env) : 12;
-    if (rounds == 0 || q.n_ckpt < 4) return cudaSuccess;
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -449,84 +550,95 @@ static cudaError_t plan_adjoint_queue(PT& q, const void* kern, int threads, size
     if (e != cudaSuccess) return e;
     long long slots = (long long)sms * per_sm;
     if (const char* es = getenv("DPS_QUEUE_SLOTS")) slots = atoll(es);
-    if (slots < 1 || groups <= slots) return cudaSuccess;
-    long long n_chunks = ((long long)rounds * slots + groups - 1) / groups;
-    if (n_chunks < 2) return cudaSuccess;
-    int chunk_ckpts = (int)((q.n_ckpt + n_chunks - 1) / n_chunks);
-    if (chunk_ckpts < 1) chunk_ckpts = 1;
-    n_chunks = (q.n_ckpt + chunk_ckpts - 1) / chunk_ckpts;
-    if (n_chunks < 2 || groups * n_chunks > 0x3fffffff) return cudaSuccess;
-    q.q_items = (int)(groups * n_chunks);
-    q.q_groups = (int)groups;
-    q.q_chunk_ckpts = chunk_ckpts;
-    *grid = (unsigned)q.q_items;
+    if (rounds > 0 && q.n_ckpt >= 4 && slots >= 1 && groups > slots) {
+        long long n_chunks = ((long long)rounds * slots + groups - 1) / groups;
+        int chunk_ckpts = (int)((q.n_ckpt + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1));
+        if (chunk_ckpts < 1) chunk_ckpts = 1;
+        n_chunks = (q.n_ckpt + chunk_ckpts - 1) / chunk_ckpts;
+        if (n_chunks >= 2 && groups * n_chunks <= 0x3fffffff) {
+            q.q_items = (int)(groups * n_chunks);
+            q.q_chunk_ckpts = chunk_ckpts;
+            *grid = (unsigned)q.q_items;
+        }
+    }
     return cudaMemsetAsync(q.q_counter, 0, sizeof(int) * (size_t)(groups + 1), stream);
 }
 
-template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER, int NGP, bool FASTPAR>
+template <class PT, int G, int CM, bool ZGRAD, int SOLVER, int NGP, int PM, bool INREG = false>
 static cudaError_t launch_bwd_one(const PT& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
     const int GG = C::WIDE ? p.n_gen : G;
     const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * GG * DPS_N_SLOTS + sizeof(short) * GG * DPS_N_SLOTS +
                         ((C::WIDE || p.z_per_sim) ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
-    auto kern = dps_adjoint_kernel<PT, G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, false>;
+    const long long spb = C::WIDE ? C::THREADS / ((p.n_gen + 31) & ~31) : (long long)C::WARPS * C::SPW;
+    const long long blocks = (p.P + spb - 1) / spb;
+    // The fast-constant builds (no network gradient: those accumulate dL/dZ in HBM across chunks) only exist as work-queue
+    // kernels; a launch that is not worth cutting into chunks runs as a queue of one chunk per block group.
+    constexpr bool Q = !ZGRAD && (PM != 0);
+    auto kern = dps_adjoint_kernel<PT, G, CM, ZGRAD, SOLVER, NGP, PM, Q, INREG>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long long spb = C::WIDE ? C::THREADS / ((p.n_gen + 31) & ~31) : (long long)C::WARPS * C::SPW;
-    const long long blocks = (p.P + spb - 1) / spb;
-    // the work-queue build exists for the common case (no network gradient: those accumulate dL/dZ in HBM across chunks)
-    if constexpr (!ZGRAD && FASTPAR) {
-        auto kern_q = dps_adjoint_kernel<PT, G, CTRL, ZGRAD, SOLVER, NGP, FASTPAR, true>;
+    if constexpr (Q) {
         PT q = p;
         unsigned grid = (unsigned)blocks;
-        cudaError_t e = plan_adjoint_queue(q, (const void*)kern_q, C::THREADS, smem, blocks, &grid, stream);
+        cudaError_t e = plan_adjoint_queue(q, (const void*)kern, C::THREADS, smem, blocks, &grid, stream);
         if (e != cudaSuccess) return e;
-        if (q.q_items > 0) {
-            if (smem > 48 * 1024) {
-                e = cudaFuncSetAttribute(kern_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-            }
-            kern_q<<<grid, C::THREADS, smem, stream>>>(q);
-            return cudaGetLastError();
-        }
+        kern<<<grid, C::THREADS, smem, stream>>>(q);
+        return cudaGetLastError();
+    } else {
+        kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+        return cudaGetLastError();
     }
-    kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
 }
 
-template <class PT, int G, bool CTRL, bool ZGRAD, int SOLVER>
+template <class PT, int G, int CM, bool ZGRAD, int SOLVER>
 static cudaError_t launch_bwd_ngp(const PT& p, int ngp, cudaStream_t stream) {
-    // accumulators for the register slots only (machine constants / set points: the usual identification leaves) or for
-    // every slot; the network-gradient variant is only built with all of them (it is the rare one)
-    // fast constants whenever the plan allows it and the common accumulator set is enough; the generic reader with all
-    // accumulators covers everything else
+    // Accumulators for the register slots only (machine constants / set points: the usual identification leaves) or for
+    // every slot; fast constants whenever the plan allows it (pmode 1 / 3); the generic reader with all accumulators
+    // covers everything else.  The network-gradient variant is only built generic (it is the rare one).  (Controller
+    // constants as constant-bank operands, the forward stepper's PMODE 3, were measured here too: no gain -- the sweep is
+    // bound by dependency latency, not by its shared-memory reads -- so the adjoint has no such build.)
     if constexpr (!ZGRAD) {
-        if (ngp <= DPS_N_REG_SLOTS && p.fast_par) return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_REG_SLOTS, true>(p, stream);
-        if (p.fast_par) return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, true>(p, stream);
+        if (ngp <= DPS_N_REG_SLOTS && p.pmode != 2) {
+            if constexpr (G != 0) {
+                if (p.ckpt_stride == 1) return launch_bwd_one<PT, G, CM, ZGRAD, SOLVER, DPS_N_REG_SLOTS, 1, true>(p, stream);
+            }
+            return launch_bwd_one<PT, G, CM, ZGRAD, SOLVER, DPS_N_REG_SLOTS, 1>(p, stream);
+        }
+        if (p.pmode != 2) return launch_bwd_one<PT, G, CM, ZGRAD, SOLVER, DPS_N_SLOTS, 1>(p, stream);
     }
-    return launch_bwd_one<PT, G, CTRL, ZGRAD, SOLVER, DPS_N_SLOTS, false>(p, stream);
+    // generic: built for bare machines and for the run-time controller mask only
+    if constexpr (CM == 7) return launch_bwd_one<PT, G, -1, ZGRAD, SOLVER, DPS_N_SLOTS, 0>(p, stream);
+    else return launch_bwd_one<PT, G, CM, ZGRAD, SOLVER, DPS_N_SLOTS, 0>(p, stream);
 }
 
-template <class PT, int G, bool CTRL, bool ZGRAD>
+template <class PT, int G, int CM, bool ZGRAD>
 static cudaError_t launch_bwd_solver(const PT& p, int ngp, cudaStream_t stream) {
-    if (p.solver == DPS_EULER) return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_EULER>(p, ngp, stream);
-    if (p.solver == DPS_HEUN) return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_HEUN>(p, ngp, stream);
-    return launch_bwd_ngp<PT, G, CTRL, ZGRAD, DPS_RK4>(p, ngp, stream);
+    if (p.solver == DPS_EULER) return launch_bwd_ngp<PT, G, CM, ZGRAD, DPS_EULER>(p, ngp, stream);
+    if (p.solver == DPS_HEUN) return launch_bwd_ngp<PT, G, CM, ZGRAD, DPS_HEUN>(p, ngp, stream);
+    return launch_bwd_ngp<PT, G, CM, ZGRAD, DPS_RK4>(p, ngp, stream);
 }
 
+// cmask: 0 = bare machines, 7 = every generator carries all three controllers, -1 = anything else
 template <int G>
-cudaError_t launch_bwd_g(const BwdParams& p, bool ctrl, int ngp, cudaStream_t stream) {
-    if (p.g_zsub != nullptr) return ctrl ? launch_bwd_solver<BwdParams, G, true, true>(p, ngp, stream) : launch_bwd_solver<BwdParams, G, false, true>(p, ngp, stream);
-    return ctrl ? launch_bwd_solver<BwdParams, G, true, false>(p, ngp, stream) : launch_bwd_solver<BwdParams, G, false, false>(p, ngp, stream);
+cudaError_t launch_bwd_g(const BwdParams& p, int cmask, int ngp, cudaStream_t stream) {
+    if (p.g_zsub != nullptr)
+        return cmask == 0 ? launch_bwd_solver<BwdParams, G, 0, true>(p, ngp, stream) : launch_bwd_solver<BwdParams, G, -1, true>(p, ngp, stream);
+    if (cmask == 0) return launch_bwd_solver<BwdParams, G, 0, false>(p, ngp, stream);
+    if (cmask == 7) return launch_bwd_solver<BwdParams, G, 7, false>(p, ngp, stream);
+    return launch_bwd_solver<BwdParams, G, -1, false>(p, ngp, stream);
 }
 
-// 17..128 generators (G = 0: run-time generator count)
-inline cudaError_t launch_bwd_wide_impl(const BwdWideParams& p, bool ctrl, int ngp, cudaStream_t stream) {
+// 17..128 generators (G = 0: run-time generator count); only instantiated by dps_backward_wide.cu
+#ifdef DPS_BWD_WIDE_TU
+inline cudaError_t launch_bwd_wide_impl(const BwdWideParams& p, int cmask, int ngp, cudaStream_t stream) {
     if (p.g_zsub != nullptr || p.z_per_sim) return cudaErrorInvalidValue;
-    return ctrl ? launch_bwd_solver<BwdWideParams, 0, true, false>(p, ngp, stream)
-                : launch_bwd_solver<BwdWideParams, 0, false, false>(p, ngp, stream);
+    if (cmask == 0) return launch_bwd_solver<BwdWideParams, 0, 0, false>(p, ngp, stream);
+    if (cmask == 7) return launch_bwd_solver<BwdWideParams, 0, 7, false>(p, ngp, stream);
+    return launch_bwd_solver<BwdWideParams, 0, -1, false>(p, ngp, stream);
 }
+#endif
 
 }  // namespace dps

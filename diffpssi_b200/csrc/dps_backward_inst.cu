@@ -7,5 +7,5 @@
 #endif
 
 namespace dps {
-template cudaError_t launch_bwd_g<DPS_G>(const BwdParams&, bool, int, cudaStream_t);
+template cudaError_t launch_bwd_g<DPS_G>(const BwdParams&, int, int, cudaStream_t);
 }

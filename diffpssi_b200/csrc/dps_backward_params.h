@@ -20,13 +20,14 @@ struct BwdParamsT {
     double* g_x0;              // [n_gen][13][P]
     double* gslot;             // [n_want][P]
     double* g_zsub;            // [n_cfg][z_rows][z_cols][2][P] accumulated, or null
-    double* scratch;           // [ckpt_stride][13][P][n_gen]
+    double* scratch;           // [ckpt_stride][P][n_gen][stages * 18]  (dps_backward.cuh)
     int n_obs, z_rows, z_cols, n_cfg, z_per_sim, ckpt_stride, n_ckpt, n_seg;
-    int fast_par;              // plan pmode 1/3: only the DPS_N_REG_SLOTS leading slots may differ per trajectory
+    int pmode;                 // plan pmode: 1/3 = only the DPS_N_REG_SLOTS leading slots may differ per trajectory, 2 = any
     int seg_step[MAX_SEG];
     int seg_cfg[MAX_SEG];
     int ctrl[MAXG];
     unsigned rec_mask[MAXG];
+    int rec_uniform;           // rec_mask identical for every generator (field tests become uniform branches)
     short rec_chan[MAXG][DPS_N_FIELDS];
     short obs_chan[MAX_EXTRA_OBS][2];
     short slot_vary[MAXG * DPS_N_SLOTS];
