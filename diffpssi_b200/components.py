@@ -16,17 +16,36 @@ live in ``prologue.py``.  Containers only (i) take the same constructor argument
 (complex128 for machine quantities, float64 for controller blocks) and (iii) expose the state /
 algebraic attributes, which the simulator fills after ``initialize()`` and after ``run()``.
 """
+import weakref
+
 import torch
 
 C128 = torch.complex128
 F64 = torch.float64
 
 
+# Tensors this package itself created by broadcasting ONE number over the batch: known to be batch-uniform without looking
+# at their contents (the prologue otherwise pays a device comparison + synchronisation per parameter tensor on its first
+# call: ~650 of them for the IEEE 39-bus grid).  Keyed by identity, valid for the version counter recorded here.
+_KNOWN_UNIFORM = {}
+
+
+def mark_uniform(t):
+    k = id(t)
+    _KNOWN_UNIFORM[k] = (weakref.ref(t, lambda _r, k=k: _KNOWN_UNIFORM.pop(k, None)), t._version)
+    return t
+
+
+def known_uniform(t):
+    hit = _KNOWN_UNIFORM.get(id(t))
+    return hit is not None and hit[0]() is t and hit[1] == t._version
+
+
 def _bcast(value, P, dtype, device):
     """Scalar (or tensor) -> [P,1] tensor.  A user-supplied tensor is kept as is (it may be an autograd leaf)."""
     if torch.is_tensor(value):
         return value
-    return torch.full((P, 1), value, dtype=dtype, device=device)
+    return mark_uniform(torch.full((P, 1), value, dtype=dtype, device=device))
 
 
 class _Component(object):
@@ -172,7 +191,7 @@ class Shunt(_Component):
 
     def enable_parallel_simulation(self, parallel_sims, device='cpu'):
         super().enable_parallel_simulation(parallel_sims, device)
-        self.y_shunt = torch.ones((parallel_sims, 1), dtype=C128, device=device) * self.y_shunt.to(device)
+        self.y_shunt = mark_uniform(torch.ones((parallel_sims, 1), dtype=C128, device=device) * self.y_shunt.to(device))
 
 
 # --------------------------------------------------------------------------------------------------

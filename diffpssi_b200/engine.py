@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DPS_B200_LIB') or os.path.join(_HERE, 'libdps_b200.so')   # override: kernel A/B experiments
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 N_STATES = 13
 N_SLOTS = 42
 N_FIELDS = 20
@@ -25,7 +25,7 @@ MAX_FAULT = 8
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes', 'dps_forward_workspace_bytes',
            'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_fp64_dmma_probe', 'dps_math_probe', 'dps_plan_info',
            'dps_last_error', 'dps_abi_version', 'dps_ident_loss_workspace_bytes', 'dps_ident_loss', 'dps_bfgs_step',
-           'dps_ident_control')
+           'dps_ident_control', 'dps_load_flow', 'dps_dynamic_inverse', 'dps_model_init')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
 CH_GEN, CH_BUS_VRE, CH_BUS_VIM = 0, 1, 2

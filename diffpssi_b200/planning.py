@@ -121,6 +121,24 @@ def common_controller_constants(init, upar, slot_vary, memo=None):
     return out
 
 
+def common_controller_constants_keyed(ctrl, upar, slot_vary, key, memo):
+    """:func:`common_controller_constants` for the kernel prologue: same answer, memoised on the identity + version of the
+    raw controller parameters (``key``) instead of on slot tensors that are new views every run."""
+    if any(f != (CTRL_AVR | CTRL_GOV | CTRL_PSS) for f in ctrl) or any(k is None for k in key):
+        return None
+    G = len(ctrl)
+    if any(slot_vary[g * N_SLOTS + k] >= 0 for g in range(G) for k in range(N_REG_SLOTS, N_SLOTS)):
+        return None
+    hit = memo.get('common_ctrl_keyed')
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    host = upar.detach().cpu()
+    tail = host[:, N_REG_SLOTS:]
+    out = [float(v) for v in host[0]] if bool((tail == tail[:1]).all()) else None
+    memo['common_ctrl_keyed'] = (key, out)
+    return out
+
+
 def observed_rows(init, channel_keys):
     """Rows of the reduced impedance matrix: the generator buses (generator order) then every recorded bus that hosts
     no generator.  Also rewrites recorder keys into (unique) C-ABI channels; ``rows[i]`` is the kernel recorder row

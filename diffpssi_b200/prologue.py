@@ -28,7 +28,7 @@ import math
 
 import torch
 
-from .components import SynchMachine, Load, Shunt
+from .components import SynchMachine, Load, Shunt, known_uniform
 
 C128 = torch.complex128
 F64 = torch.float64
@@ -85,6 +85,8 @@ class _Cols(object):
         if collapse and t.shape[0] == P and P > 1 and not t.requires_grad:
             hit = self.cache.get(id(value))
             if hit is not None and hit[0] is value and hit[1] == value._version:
+                return t[:1]
+            if known_uniform(value):
                 return t[:1]
             if bool((t == t[:1]).all()):
                 self.cache[id(value)] = (value, value._version)
@@ -255,7 +257,7 @@ def load_flow(sim, col, y_bus, max_iter=600, tol=1e-8):
 # ==================================================================================================
 class InitResult(object):
     """What the time loop consumes."""
-    __slots__ = ('gens', 'gen_bus', 'ctrl', 'x0', 'slots', 'xst', 'Z0', 'Ydiag', 'bus_v', 's_calc', 'lf_iters')
+    __slots__ = ('gens', 'gen_bus', 'ctrl', 'x0', 'slots', 'xst', 'Z0', 'Ydiag', 'bus_v', 's_calc', 'lf_iters', 'inj0')
 
 
 def _clamp(x, lo, hi):

@@ -17,10 +17,10 @@ import time as _time
 import numpy as np
 import torch
 
-from . import adjoint, engine, planning, prologue, recording
+from . import adjoint, engine, planning, prologue, prologue_device, recording
 from .autograd import StepFunction
 from .components import (Bus, Line, Transformer, Load, Shunt, SynchMachine, SEXS, TGOV1, STAB1, ScEvent,
-                         ParamEvent)
+                         ParamEvent, mark_uniform)
 
 SOLVERS = ('euler', 'heun', 'rk4')            # solvers.py:226-230
 BACKEND = os.environ.get('DIFFPSSI_FORCE_SIM_BACKEND', 'cuda')      # backend.py:11-14
@@ -212,7 +212,7 @@ class PowerSystemSimulation(object):
         P = self.parallel_sims
         if getattr(self, '_flat_start', None) is None:
             # one shared (never written) tensor, so that the prologue's memoisation sees the same input after every reset
-            self._flat_start = torch.ones((P, 1), dtype=torch.complex128, device=self.prologue_device)
+            self._flat_start = mark_uniform(torch.ones((P, 1), dtype=torch.complex128, device=self.prologue_device))
         for bus in self.busses:
             v = getattr(bus.models[-1], 'v_soll', None) if bus.models else None
             bus.voltage = v if v is not None else self._flat_start
@@ -230,17 +230,28 @@ class PowerSystemSimulation(object):
                     raise NotImplementedError("bus model %r on %s has no kernel implementation: backend='cuda' integrates "
                                               'SynchMachine (+ SEXS / TGOV1 / STAB1), constant-impedance loads and shunts'
                                               % (type(m).__name__, bus.name))
-        init = prologue.initialize(self, self.prologue_device)
+        # kernels of libdps_b200.so when nothing needs a gradient through the prologue (prologue_device.py), else the
+        # differentiable torch restatement
+        init = None
+        if prologue_device.applicable(self, self.prologue_device):
+            init = prologue_device.initialize(self, self.prologue_device)
+        self.last_prologue = 'kernels' if init is not None else 'torch'
+        if init is None:
+            init = prologue.initialize(self, self.prologue_device)
         self.inverse_dynamic_y_matrix = init.Z0
         P = self.parallel_sims
-        cur = prologue.initial_injections(init)                                   # [B,G]
-        B = max(cur.shape[0], init.Z0.shape[0])
-        n = len(self.busses)
-        inj = torch.zeros((B, n), dtype=torch.complex128, device=self.prologue_device)
-        cols = [inj[:, i] for i in range(n)]
-        for gi, b in enumerate(init.gen_bus):
-            cols[b] = cols[b] + cur[:, gi]
-        inj = torch.stack(cols, dim=1)
+        packed = getattr(init, 'packed', None)
+        if packed is not None:
+            inj = packed['inj_bus']                                               # [B,n] from the kernel path
+        else:
+            cur = prologue.initial_injections(init)                               # [B,G]
+            B = max(cur.shape[0], init.Z0.shape[0])
+            n = len(self.busses)
+            inj = torch.zeros((B, n), dtype=torch.complex128, device=self.prologue_device)
+            cols = [inj[:, i] for i in range(n)]
+            for gi, b in enumerate(init.gen_bus):
+                cols[b] = cols[b] + cur[:, gi]
+            inj = torch.stack(cols, dim=1)
         volt = torch.matmul(init.Z0, inj.unsqueeze(-1)).squeeze(-1)               # simulator.py:447
         for i, bus in enumerate(self.busses):
             bus.voltage = volt[:, i:i + 1].expand(P, 1)
@@ -284,18 +295,29 @@ class PowerSystemSimulation(object):
         init = self.initialize()
         P, dev, pdev = self.parallel_sims, self.device, self.prologue_device
         rplan = self._trace_recorder(init)
+        packed = getattr(init, 'packed', None)             # kernel prologue: inputs already in the stepping kernel's layout
         net_grad = torch.is_grad_enabled() and (init.Z0.requires_grad or init.Ydiag.requires_grad)
-        needs_grad = net_grad or (torch.is_grad_enabled() and (
+        needs_grad = packed is None and (net_grad or (torch.is_grad_enabled() and (
             any(t.requires_grad for x in init.x0 for t in x) or
-            any(v.requires_grad for sl in init.slots for v in sl.values())))
+            any(v.requires_grad for sl in init.slots for v in sl.values()))))
         topo, extras = planning.build_topology(self, init, rplan.channel_keys, self.solver,
                                                self._checkpoint_stride(len(init.gens)) if needs_grad else 0)
-        x0 = planning.canonical_x0(init, P)
-        upar, vpar, slot_vary = planning.pack_slots(init, P, pdev, self.__dict__.setdefault('_pack_cache', {}))
+        pack_cache = self.__dict__.setdefault('_pack_cache', {})
+        if packed is not None:
+            G = len(init.gens)
+            x0 = packed['x0'] if packed['x0'].shape[-1] == P else packed['x0'].expand(G, engine.N_STATES, P).contiguous()
+            upar = packed['slots'][:, :, 0].contiguous()
+            vpar = None if packed['vrows'] is None else packed['slots'].reshape(G * engine.N_SLOTS, -1).index_select(0, packed['vrows'])
+            slot_vary = packed['slot_vary']
+            topo['common_ctrl'] = planning.common_controller_constants_keyed(init.ctrl, upar, slot_vary, packed['ctrl_key'],
+                                                                              pack_cache)
+        else:
+            x0 = planning.canonical_x0(init, P)
+            upar, vpar, slot_vary = planning.pack_slots(init, P, pdev, pack_cache)
+            topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary, pack_cache)
         topo['slot_vary'] = slot_vary
         topo['n_vary'] = 0 if vpar is None else vpar.shape[0]
         topo['want'] = adjoint.wanted_slots(init, prologue.SLOTS) if needs_grad else None
-        topo['common_ctrl'] = planning.common_controller_constants(init, upar, slot_vary, self._pack_cache)
         topo['want_z'] = bool(net_grad)
         plan = engine.Plan(topo)
         self.last_plan = plan

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DPS_ABI_VERSION 3
+#define DPS_ABI_VERSION 4
 
 /* ---- per-generator state layout (canonical: absent controllers keep zero slots) ----------------------------
  * reference order: machine(6) | exciter(lead-lag, PT1) | governor(PT1, lead-lag) | PSS(washout, LL1, LL2)
@@ -246,6 +246,61 @@ int dps_bfgs_step(int64_t P, int32_t n, double* const* x, const int32_t* x_strid
 /* dps_ident_control: ps_optimization.py:246-249 on the device state:
  *     if last_min_loss and last_min_loss < cur_min_loss: max_step *= decay;   last_min_loss = cur_min_loss */
 int dps_ident_control(double* state, double decay, void* stream);
+
+/* ---- initialize() on the device ----------------------------------------------------------
+ * What PowerSystemSimulation.run() does before the time loop (simulator.py:438-450), for callers that need no autograd
+ * graph through it.  Complex arrays are interleaved (re, im) pairs -- torch.complex128 memory -- with the batch index
+ * OUTERMOST ([B][n]...); a batch size argument of 1 means "shared by all B rows".  Networks of up to 64 buses (dense
+ * workspaces live in shared memory); rc 2 = outside the supported size, the caller keeps its own path.               */
+enum dps_bus_type { DPS_BUS_SLACK = 0, DPS_BUS_PV = 1, DPS_BUS_PQ = 2 };          /* load_flow.py:37-60 */
+
+/* raw model parameters of one generator, as the reference's model constructors hold them
+ * (synchronous_machine.py:31-84, exciters.py:35-72, governors.py:35-75, stabilizers.py:35-73)                        */
+enum dps_raw {
+    DPS_RAW_SN = 0, DPS_RAW_SN_SYS, DPS_RAW_XD, DPS_RAW_XQ, DPS_RAW_XDT, DPS_RAW_XQT, DPS_RAW_XDST, DPS_RAW_XQST,
+    DPS_RAW_TD0T, DPS_RAW_TQ0T, DPS_RAW_TD0ST, DPS_RAW_TQ0ST, DPS_RAW_H, DPS_RAW_D,
+    /* SEXS: lead-lag T_1 (T_a), T_2 (T_b); PT1Limited T (T_e), gain K, limits; voltage set point */
+    DPS_RAW_A_T1, DPS_RAW_A_T2, DPS_RAW_A_TE, DPS_RAW_A_K, DPS_RAW_A_EMIN, DPS_RAW_A_EMAX, DPS_RAW_A_VSET,
+    /* TGOV1: PT1Limited T (T_1), gain 1/R, limits; lead-lag T_1 (T_2), T_2 (T_3); D_t */
+    DPS_RAW_G_T1, DPS_RAW_G_GAIN, DPS_RAW_G_VMIN, DPS_RAW_G_VMAX, DPS_RAW_G_T2, DPS_RAW_G_T3, DPS_RAW_G_DT,
+    /* STAB1: washout K_w, T_w; lead-lag 1 (T_1, T_2), lead-lag 2 (T_1, T_2) as stabilizers.py:71-72 wires them; limit */
+    DPS_RAW_S_KW, DPS_RAW_S_TW, DPS_RAW_S_LL1_T1, DPS_RAW_S_LL1_T2, DPS_RAW_S_LL2_T1, DPS_RAW_S_LL2_T2, DPS_RAW_S_HLIM,
+    DPS_N_RAW
+};
+
+/* dps_load_flow: polar Newton-Raphson power flow (load_flow.py:9-179), one thread block per batch row: mismatch,
+ * Jacobian, dense solve with partial pivoting and the polar update of one iteration are one kernel launch.  Same unknown
+ * ordering (angles of PV then PQ buses, magnitudes of PQ buses), update sequence and stopping rule as the reference:
+ * iterate until the batch-global max |mismatch| of the PRE-update iterate is below tol (load_flow.py:147-167) -- a host
+ * decision, so this entry point SYNCHRONISES the stream once per iteration (the one exception to "no hidden
+ * synchronisation"; it is a once-per-run prologue call).  rc 4 = no convergence after max_iter iterations.
+ *   bus_type   HOST [n_bus] dps_bus_type            y_static  [By][n][n] complex       s_soll  [Bs][n] complex
+ *   v_init     [Bv][n] complex (flat start / set points)       v_out, s_out  [B][n] complex (voltage, calculated power)
+ *   worst      device scratch, one double            iters     HOST out: iterations after the first                   */
+int dps_load_flow(int32_t n_bus, const int32_t* bus_type, int64_t B, const double* y_static, int64_t By,
+                  const double* s_soll, int64_t Bs, const double* v_init, int64_t Bv, double* v_out, double* s_out,
+                  double* worst, double tol, int32_t max_iter, int32_t* iters, void* stream);
+
+/* dps_dynamic_inverse: loads become constant admittances from the load-flow voltage, y = 1 / conj(|v|^2 / s_load)
+ * (static_models.py:515-527), are added to the diagonal of y_base (branches, shunts, generator Norton admittances:
+ * simulator.py:400-422), and Z0 = inv(Y_dyn) (simulator.py:386) by complex Gauss-Jordan elimination with partial
+ * pivoting, one thread block per batch row.
+ *   load_bus  HOST [n_load]     s_load [Bl][n_load] complex (per unit)     v [Bv][n] complex
+ *   y_load    out [B][n_load] complex    y_diag  out [B][n] complex (diagonal of Y_dyn)    z0  out [B][n][n] complex */
+int dps_dynamic_inverse(int32_t n_bus, int64_t B, const double* y_base, int64_t By, int32_t n_load, const int32_t* load_bus,
+                        const double* s_load, int64_t Bl, const double* v, int64_t Bv, double* y_load, double* y_diag,
+                        double* z0, void* stream);
+
+/* dps_model_init: initial states (canonical dps_state layout), derived constants (dps_slot) and the Norton current at
+ * x0 of every (trajectory, generator): synchronous_machine.py:279-323, 256-260; exciters.py:129-138;
+ * governors.py:136-145; stabilizers.py:135-145; blocks.py:196-207, 332-342, 426-436.  Any number of buses up to 32767.
+ *   gen_bus, ctrl  HOST [n_gen] (bus index, dps_ctrl flags)      v, s  [Bv|Bs][n_bus] complex load-flow voltage / power
+ *   raw_u     [n_gen][DPS_N_RAW] batch-uniform raw parameters    raw_vary  HOST [n_gen][DPS_N_RAW]: -1 or row of raw_v
+ *   raw_v     [n_rv][B] per-trajectory raw parameters (may be NULL when nothing varies)
+ *   x0   out [n_gen][13][B]      slots  out [n_gen][DPS_N_SLOTS][B]      inj  out [n_gen][2][B] (re, im)              */
+int dps_model_init(int32_t n_gen, int32_t n_bus, int64_t B, const int32_t* gen_bus, const int32_t* ctrl, const double* v,
+                   int64_t Bv, const double* s, int64_t Bs, const double* raw_u, const int32_t* raw_vary, const double* raw_v,
+                   double* x0, double* slots, double* inj, void* stream);
 
 /* Measurement helper: runs a dependent-chain-free DFMA loop on every SM and returns the achieved fp64
  * TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises.  Used by bench.py as the fp64 roofline denominator

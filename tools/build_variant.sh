@@ -7,7 +7,7 @@ name=$1; shift
 cd "$(dirname "$0")/../diffpssi_b200/csrc"
 out=../../gpurun_variants; mkdir -p $out/obj_$name
 F="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v -DDPS_ONLY_G10 $*"
-for s in dps_abi dps_forward dps_forward_wide dps_network dps_backward dps_backward_wide dps_optim; do
+for s in dps_abi dps_forward dps_forward_wide dps_network dps_backward dps_backward_wide dps_optim dps_prologue; do
   nvcc $F -c $s.cu -o $out/obj_$name/$s.o 2> $out/obj_$name/$s.log &
 done
 nvcc $F -DDPS_G=10 -c dps_forward_inst.cu -o $out/obj_$name/g10.o 2> $out/obj_$name/g10.log &
