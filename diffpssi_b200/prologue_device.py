@@ -9,9 +9,9 @@ no such gradient goes through three kernels of ``libdps_b200.so`` instead (``csr
                          simulator.py:386, 400-422
     dps_model_init       synchronous_machine.py:279-323 + controller initialisations: x0, constant slots, Norton currents
 
-The admittance matrices themselves (branches, shunts, generator Norton admittances) are still assembled by
-``prologue.static_admittance`` / ``dynamic_base`` -- a few dozen scatter operations on ``[B,n,n]`` with B = 1 when the
-network is shared -- and memoised like the torch path's.  Everything returned has the structure of
+The admittance matrices themselves (branches, shunts, generator Norton admittances) are assembled by a handful of small
+matrix products with 0/1 incidence matrices (``_Network``) -- ``[B,n,n]`` with B = 1 when the network is shared -- and
+memoised like the torch path's.  Everything returned has the structure of
 ``prologue.InitResult`` (``[B,1]`` views with B in {1, P}; which quantities are per-trajectory follows from which raw
 parameters are), so planning, packing, recorder tracing and the oracle harness do not care which path produced it.
 Agreement with the torch prologue: <= 1e-12 on every state, constant and matrix entry (tests/test_cuda_prologue.py); the
@@ -97,19 +97,105 @@ def _raw_attrs(g):
     return v
 
 
-def dynamic_base(sim, col):
-    """Dynamic admittance without the loads: branches + shunts + generator Norton admittances (simulator.py:400-422;
-    the loads are added on the device from the load-flow voltage)."""
-    diag = []
-    for bus in sim.busses:
-        c = []
-        for m in bus.models:
-            if isinstance(m, Shunt):
-                c.append(col(m.y_shunt, C128))
-            elif isinstance(m, SynchMachine):
-                c.append(-1j / col(m.x_d_st, C128) * (col(m.s_n, C128) / m.s_n_sys))
-        diag.append(c)
-    return prologue._assemble(sim, col, diag)
+def _cat_cols(cols):
+    """[B,1] columns (B in {1, P}) -> [B,K]."""
+    B = max(c.shape[0] for c in cols)
+    return torch.cat([c.expand(B, 1) for c in cols], dim=1)
+
+
+def _incidence(index, n, dev):
+    m = torch.zeros((len(index), n), dtype=C128, device=dev)
+    if index:
+        m[torch.arange(len(index), device=dev), torch.tensor(index, device=dev)] = 1
+    return m
+
+
+class _Network(object):
+    """Vectorised assembly of the admittance matrices and scheduled injections for the kernel path: the same terms as
+    ``prologue._branch_terms`` / ``_assemble`` (simulator.py:362-384, 400-422), accumulated as a handful of small matrix
+    products with 0/1 incidence matrices instead of one scatter per branch (deterministic, ~40 launches instead of ~1500;
+    sums in a different order than the torch path: agreement ~1e-16 relative)."""
+
+    def __init__(self, sim, dev):
+        n = len(sim.busses)
+        branches = list(sim.lines) + list(sim.trafos)
+        self.F = _incidence([b.from_bus_id for b in branches], n, dev)
+        self.T = _incidence([b.to_bus_id for b in branches], n, dev)
+        nl = len(sim.lines)
+        self.num = torch.tensor([1.0] * nl + [float(t.s_n) for t in sim.trafos], dtype=F64, device=dev)
+        self.den = torch.tensor([1.0] * nl + [float(t.s_n_sys) for t in sim.trafos], dtype=F64, device=dev)
+        self.shunts = [(bi, m) for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, Shunt)]
+        self.gens = [(bi, m) for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, SynchMachine)]
+        self.loads = [(bi, m) for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, Load)]
+        self.inc_shunt = _incidence([bi for bi, _ in self.shunts], n, dev)
+        self.inc_gen = _incidence([bi for bi, _ in self.gens], n, dev)
+        self.inc_load = _incidence([bi for bi, _ in self.loads], n, dev)
+        self.sys_gen = torch.tensor([float(m.s_n_sys) for _, m in self.gens], dtype=F64, device=dev)
+        self.sys_load = torch.tensor([float(m.s_n_sys) for _, m in self.loads], dtype=F64, device=dev)
+        self.key = (tuple((b.from_bus_id, b.to_bus_id) for b in branches), tuple(bi for bi, _ in self.shunts),
+                    tuple(bi for bi, _ in self.gens), tuple(bi for bi, _ in self.loads))
+        self.n, self.dev = n, dev
+
+    def branches(self, sim, col):
+        """[n,n] of lines and transformers (their parameters are read from the LAST trajectory: the reference's scatter with
+        duplicate index tensors, static_models.py:321-322)."""
+        br = list(sim.lines) + list(sim.trafos)
+        if not br:
+            return torch.zeros((self.n, self.n), dtype=C128, device=self.dev)
+        r = torch.cat([col(b.r, F64, last_row=True) for b in br]).reshape(-1)
+        x = torch.cat([col(b.x, F64, last_row=True) for b in br]).reshape(-1)
+        bb = torch.cat([col(b.b, F64, last_row=True) for b in br]).reshape(-1)
+        series = 1 / (r + 1j * x)
+        y_off = (-series * self.num / self.den).unsqueeze(1)
+        y_diag = ((series + 1j * bb / 2) * self.num / self.den).unsqueeze(1)
+        Ft, Tt = self.F.t(), self.T.t()
+        return Ft @ (y_off * self.T) + Tt @ (y_off * self.F) + Ft @ (y_diag * self.F) + Tt @ (y_diag * self.T)
+
+    def static(self, yb, col):
+        """Load-flow admittance [B,n,n]: branches + shunts."""
+        if not self.shunts:
+            return yb.unsqueeze(0)
+        d = _cat_cols([col(m.y_shunt, C128) for _, m in self.shunts]) @ self.inc_shunt
+        return yb.unsqueeze(0) + torch.diag_embed(d)
+
+    def dynamic_base(self, yb, col):
+        """Dynamic admittance without the loads [B,n,n]: + generator Norton admittances -j/x_d'' * S_n/S_sys
+        (synchronous_machine.py:336)."""
+        d = None
+        if self.shunts:
+            d = _cat_cols([col(m.y_shunt, C128) for _, m in self.shunts]) @ self.inc_shunt
+        if self.gens:
+            xdst = _cat_cols([col(m.x_d_st, C128) for _, m in self.gens])
+            sn = _cat_cols([col(m.s_n, C128) for _, m in self.gens])
+            g = (-1j / xdst * (sn / self.sys_gen)) @ self.inc_gen
+            d = g if d is None else d + g
+        return yb.unsqueeze(0) if d is None else yb.unsqueeze(0) + torch.diag_embed(d)
+
+    def scheduled(self, col):
+        """Scheduled bus injections [B,n] (static_models.py:165-176; synchronous_machine.py:347; static_models.py:495)."""
+        s = torch.zeros((1, self.n), dtype=C128, device=self.dev)
+        if self.gens:
+            s = s + (_cat_cols([col(m.p_soll_mw, C128) for _, m in self.gens]) / self.sys_gen) @ self.inc_gen
+        if self.loads:
+            s = s + (-(self.load_power(col)) @ self.inc_load)
+        return s
+
+    def load_power(self, col):
+        """Per-unit complex power of every load [B,L]."""
+        p = _cat_cols([col(m.p_soll_mw, F64) for _, m in self.loads])
+        q = _cat_cols([col(m.q_soll_mvar, F64) for _, m in self.loads])
+        return (p + 1j * q) / self.sys_load
+
+
+def _network_of(sim, cache, dev):
+    net = cache.get('net_dev')
+    key = (tuple((b.from_bus_id, b.to_bus_id) for b in list(sim.lines) + list(sim.trafos)),
+           tuple(bi for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, Shunt)),
+           tuple(bi for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, SynchMachine)),
+           tuple(bi for bi, bus in enumerate(sim.busses) for m in bus.models if isinstance(m, Load)))
+    if net is None or net.key != key or net.dev != dev:
+        net = cache['net_dev'] = _Network(sim, dev)
+    return net
 
 
 def applicable(sim, device):
@@ -187,28 +273,15 @@ def initialize(sim, device):
             lf_cached = True
         else:
             lf_cached = False
-            y_static = prologue.static_admittance(sim, col).contiguous()
+            net = _network_of(sim, cache, dev)
+            yb = net.branches(sim, col)
+            y_static = net.static(yb, col).contiguous()
             types = {'SL': 0, 'PV': 1, 'PQ': 2}
             bus_type = (ctypes.c_int32 * n)(*[types[b.lf_type] for b in sim.busses])
-            # scheduled injections (static_models.py:165-176; synchronous_machine.py:347; static_models.py:495)
-            s_parts = []
-            for bus in sim.busses:
-                s = None
-                for m in bus.models:
-                    if isinstance(m, SynchMachine):
-                        t = (col(m.p_soll_mw, C128) + 1j * 0) / m.s_n_sys
-                    elif isinstance(m, Load):
-                        t = -(col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys
-                    else:
-                        continue
-                    s = t if s is None else s + t
-                s_parts.append(torch.zeros((1, 1), dtype=C128, device=dev) if s is None else s)
-            v_parts = [col(b.voltage, C128) for b in sim.busses]
-            Bs = max(s.shape[0] for s in s_parts)
-            Bv = max(v.shape[0] for v in v_parts)
+            s_soll = net.scheduled(col).contiguous()
+            v_init = _cat_cols([col(b.voltage, C128) for b in sim.busses]).contiguous()
+            Bs, Bv = s_soll.shape[0], v_init.shape[0]
             B = max(y_static.shape[0], Bs, Bv)
-            s_soll = torch.cat([s.expand(Bs, 1) for s in s_parts], dim=1).contiguous()
-            v_init = torch.cat([v.expand(Bv, 1) for v in v_parts], dim=1).contiguous()
             V = torch.empty((B, n), dtype=C128, device=dev)
             s_calc = torch.empty((B, n), dtype=C128, device=dev)
             worst = torch.zeros(1, dtype=F64, device=dev)
@@ -229,12 +302,12 @@ def initialize(sim, device):
         if hit is not None and lf_cached and hit['key'] == dyn_key:
             y_load, res.Ydiag, res.Z0 = hit['out']
         else:
-            y_base = dynamic_base(sim, col).contiguous()
+            net = _network_of(sim, cache, dev)
+            y_base = net.dynamic_base(net.branches(sim, col), col).contiguous()
             nl = len(loads)
             if nl:
-                s_cols = [(col(m.p_soll_mw, F64) + 1j * col(m.q_soll_mvar, F64)) / m.s_n_sys for _, m in loads]
-                Bl = max(s.shape[0] for s in s_cols)
-                s_load = torch.cat([s.expand(Bl, 1) for s in s_cols], dim=1).contiguous()
+                s_load = net.load_power(col).contiguous()
+                Bl = s_load.shape[0]
             else:
                 Bl, s_load = 1, None
             Bd = max(y_base.shape[0], Bl, V.shape[0])
@@ -334,16 +407,17 @@ def initialize(sim, device):
         res._lazy = views
 
         # expose initial values on the containers, as the reference does (complex, like its own attributes)
-        xc = torch.complex(x0, torch.zeros_like(x0))
-        sc = torch.complex(slots, torch.zeros_like(slots))
+        xc = x0[:, :6, :].to(C128)                                                 # machine states
+        exposed = ('pm0', 'efd0', 'a_bias', 'g_pref')
+        sc = slots[:, [SLOT_INDEX[k] for k in exposed], :].to(C128)
         for gi, g in enumerate(res.gens):
             _, xv, _, sv = cls[gi]
             cx = [xc[gi, k, :(B if xv[k] else 1)].reshape(-1, 1) for k in range(6)]
             g.omega, g.delta, g.e_q_t, g.e_d_t, g.e_q_st, g.e_d_st = cx
-            g.p_m = sc[gi, SLOT_INDEX['pm0'], :(B if sv['pm0'] else 1)].reshape(-1, 1)
-            g.e_fd = sc[gi, SLOT_INDEX['efd0'], :(B if sv['efd0'] else 1)].reshape(-1, 1)
+            g.p_m = sc[gi, 0, :(B if sv['pm0'] else 1)].reshape(-1, 1)
+            g.e_fd = sc[gi, 1, :(B if sv['efd0'] else 1)].reshape(-1, 1)
             if g.exciter:
-                g.exciter.bias = sc[gi, SLOT_INDEX['a_bias'], :(B if sv['a_bias'] else 1)].reshape(-1, 1)
+                g.exciter.bias = sc[gi, 2, :(B if sv['a_bias'] else 1)].reshape(-1, 1)
             if g.governor:
-                g.governor.p_ref = sc[gi, SLOT_INDEX['g_pref'], :(B if sv['g_pref'] else 1)].reshape(-1, 1)
+                g.governor.p_ref = sc[gi, 3, :(B if sv['g_pref'] else 1)].reshape(-1, 1)
     return res
