@@ -37,13 +37,14 @@ R = {n: i for i, n in enumerate(RAW)}
 
 # which raw parameters (and 'base' = load-flow voltage / power of the generator bus, S_n, X_q) every output depends on:
 # an output differs per trajectory iff one of its inputs does (the torch path gets the same answer from broadcasting)
-_BASE = ('base', 's_n', 's_n_sys', 'x_q')
+_PM = ('base', 's_n', 's_n_sys')               # p_m = Re(S) / (S_n / S_sys)
+_BASE = _PM + ('x_q',)                         # delta, i_d, i_q, v_d, v_q: e = v + j x_q i
 _EFD = _BASE + ('x_d_t', 'x_d')
 SLOT_DEPS = {
     'inv_2h': ('h',), 'd': ('d',), 'inv_td0t': ('t_d0_t',), 'xd_xdt': ('x_d', 'x_d_t'), 'inv_tq0t': ('t_q0_t',),
     'xq_xqt': ('x_q', 'x_q_t'), 'inv_td0st': ('t_d0_st',), 'xdt_xdst': ('x_d_t', 'x_d_st'), 'inv_tq0st': ('t_q0_st',),
     'xqt_xqst': ('x_q_t', 'x_q_st'), 'inv_xdst': ('x_d_st',), 'inv_xqst': ('x_q_st',), 'snr': ('s_n', 's_n_sys'),
-    'pm0': _BASE, 'efd0': _EFD, 'a_vset': ('a_vset',), 'a_bias': _EFD + ('a_k',), 'g_pref': _BASE + ('g_gain',),
+    'pm0': _PM, 'efd0': _EFD, 'a_vset': ('a_vset',), 'a_bias': _EFD + ('a_k',), 'g_pref': _PM + ('g_gain',),
     'a_r': ('a_t1', 'a_t2'), 'a_omr': ('a_t1', 'a_t2'), 'a_inv_tb': ('a_t2',), 'a_inv_te': ('a_te',), 'a_k': ('a_k',),
     'a_emin': ('a_emin',), 'a_emax': ('a_emax',),
     'g_inv_t1': ('g_t1',), 'g_gain': ('g_gain',), 'g_vmin': ('g_vmin',), 'g_vmax': ('g_vmax',), 'g_r': ('g_t2', 'g_t3'),
@@ -54,7 +55,7 @@ SLOT_DEPS = {
 }
 # canonical state rows (include/dps.h enum dps_state)
 X0_DEPS = (_BASE, _BASE, _BASE + ('x_d_t',), _BASE + ('x_q_t',), _BASE + ('x_d_st',), _BASE + ('x_q_st',),
-           _EFD + ('a_k',), _EFD + ('a_emin', 'a_emax'), _BASE + ('g_vmin', 'g_vmax'), _BASE, _EFD, _EFD, _EFD)
+           _EFD + ('a_k',), _EFD + ('a_emin', 'a_emax'), _PM + ('g_vmin', 'g_vmax'), _PM, _EFD, _EFD, _EFD)
 AVR_SLOTS = ('a_vset', 'a_bias', 'a_r', 'a_omr', 'a_inv_tb', 'a_inv_te', 'a_k', 'a_emin', 'a_emax')
 GOV_SLOTS = ('g_pref', 'g_inv_t1', 'g_gain', 'g_vmin', 'g_vmax', 'g_r', 'g_omr', 'g_inv_t3', 'g_dt')
 PSS_SLOTS = ('s_inv_tw', 's_kw', 's_r1', 's_omr1', 's_inv_t3', 's_r2', 's_omr2', 's_inv_t4', 's_hlim')

@@ -226,3 +226,43 @@ def test_network_reduce_torch_matches_device_code():
                             (ci * len(ptr))(*ptr), (ci * len(flat))(*flat), ctypes.c_double(planning.FAULT_ADMITTANCE), p_(ref))
     no, ng = len(obs_bus), len(gen_bus)
     assert np.abs(mine[:, :no, :ng] - ref[:, :no, :ng]).max() < 1e-12
+
+
+@pytest.mark.parametrize('grid,names', [
+    ('k2a', [('G1', 'h'), ('G2', 'd'), ('G3', 'x_d_t'), ('G4', 'x_q')]),
+    ('k2a', [('G1', 'x_d_st'), ('G2', 's_n')]),
+    ('ibb_wc', [('G1', 'x_d'), ('G1', 'exciter.pt1_lim.gain_pt1')]),
+    ('k2a', [('G2', 'governor.pt1_lim.gain_pt1'), ('G3', 'stabilizer.washout.k_w'), ('G1', 'exciter.lead_lag.t_1'),
+             ('G4', 'stabilizer.lead_lag2.t_2'), ('G4', 'governor.lead_lag.t_2')]),
+    ('ieee9', [('G2', 'h'), ('G3', 'x_q_st'), ('G1', 't_d0_t')]),
+])
+def test_device_prologue_classification_matches_broadcasting(grid, names):
+    """The kernel prologue (prologue_device.py) decides which initial states and constant slots differ per trajectory from a
+    static dependency table; the torch prologue gets the same answer from broadcasting.  Host logic: checked here without a GPU."""
+    from diffpssi_b200 import prologue_device as pd
+    P = 5
+    sim = Pss(parallel_sims=P, sim_time=0.1, time_step=0.005, solver='heun', grid_data=helpers.load_grid(grid), verbose=False,
+              device='cpu')
+    rng = np.random.RandomState(3)
+    ov = {}
+    for gname, attr in names:
+        obj, name = helpers.resolve_attr(sim, gname, attr)
+        old = getattr(obj, name)
+        base = float(old.reshape(-1)[0].real) if torch.is_tensor(old) else float(old)
+        ov[(gname, attr)] = base * rng.uniform(0.95, 1.05, P)
+    helpers.apply_overrides(sim, ov)
+    init = sim.initialize()                                                      # torch path (no CUDA device here)
+    col = prologue._Cols(P, 'cpu')
+    gens = prologue.generators_of(sim)
+    vary = tuple(a is not None and col(a, torch.float64).shape[0] > 1 for _, g in gens for a in pd._raw_attrs(g))
+    base_vary = init.bus_v.shape[0] > 1 or init.s_calc.shape[0] > 1
+    cls = pd._classification(vary, base_vary, init.ctrl)
+    for gi, (rows, xv, slot_names, sv) in enumerate(cls):
+        assert len(rows) == len(init.x0[gi])
+        for k, t in zip(rows, init.x0[gi]):
+            if k in (0, 10, 11, 12):
+                continue                         # identically zero rows: their batch shape carries no information
+            assert (t.shape[0] > 1) == xv[k], (gi, k)
+        assert set(slot_names) == set(init.slots[gi])
+        for name in slot_names:
+            assert (init.slots[gi][name].shape[0] > 1) == sv[name], (gi, name)
