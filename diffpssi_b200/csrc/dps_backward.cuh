@@ -25,12 +25,23 @@ namespace dps {
 #ifndef DPS_BWD_L1PF
 #define DPS_BWD_L1PF 1             // prefetch the next scratch block towards L1 while a stage is transposed
 #endif
+#ifndef DPS_BWD_ASYNC
+#define DPS_BWD_ASYNC 1            // sweep: the next stage record is copied global -> shared asynchronously (cp.async) while a stage is transposed
+#endif
 #ifndef DPS_BWD_WARPS
 #define DPS_BWD_WARPS 4            // warps per block of the (<= 16 generator) adjoint
 #endif
 #ifndef DPS_BWD_MIN_BLOCKS
 #define DPS_BWD_MIN_BLOCKS 2       // resident 128-thread blocks per SM the register allocation aims at (A/B: tools/build_variant.sh)
 #endif
+
+__device__ __forceinline__ void dps_cp_async8(double* smem, const double* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void dps_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void dps_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int G>
 struct BwdCfg {
@@ -90,6 +101,8 @@ dps_adjoint_kernel(const PT p) {
     double* s_znr = s_zti + n_cfg_s * G * G;
     double* s_zni = s_znr + n_cfg_s * G * G;
     short* s_vary = reinterpret_cast<short*>(s_zni + n_cfg_s * G * G);           // [G][DPS_N_SLOTS]
+    // staging area of the sweep: [2][SST][THREADS] doubles, one stage record per buffer, a column per thread (see below)
+    double* s_stage = reinterpret_cast<double*>(smem_raw + p.stage_offset) + threadIdx.x;
 
     const int lane = WIDE ? (int)threadIdx.x : (int)(threadIdx.x & 31);          // index into the exchange line
     const int warp = threadIdx.x >> 5;
@@ -341,6 +354,35 @@ dps_adjoint_kernel(const PT p) {
         // (seg / cfg are those of step k1 - 1, where the re-integration stopped)
         int seg_lo = p.seg_step[seg];
         const double* srec = sbase + (long long)(k1 - 1 - k0) * sstep;
+#if DPS_BWD_ASYNC && !DPS_BWD_AOS
+        // The stage records are staged through shared memory with cp.async, one record ahead: while a stage is transposed
+        // the record the sweep needs next (the previous stage, or the last stage of the previous step) is already on its
+        // way from L2, so its latency is off the dependency chain (it was 25 % of the kernel's stall samples).  Every
+        // thread copies and reads only its own column: no barrier, cp.async.wait_group orders copy and read.
+        constexpr bool STAGED = !INREG;
+        int sbuf = 0;
+        auto stage_fetch = [&](const double* rec_ptr, int b) {
+            double* dst = s_stage + (long long)b * SST * Cfg::THREADS;
+#pragma unroll
+            for (int k = 0; k < NS + 4; ++k) dps_cp_async8(dst + k * Cfg::THREADS, rec_ptr + k * srow_stride);
+            dps_cp_async_commit();
+        };
+        // ... and so are the cotangents of the recorded states, one step ahead (their load sat at the head of every step)
+        double* const s_rec = s_stage + (long long)2 * SST * Cfg::THREADS;              // [2][NS][THREADS]
+        int rbuf = 0;
+        auto rec_fetch = [&](int st, int b) {
+            const double* gr = p.grad_rec + (long long)st * P + s;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (rec_mask_u & (1u << k)) dps_cp_async8(s_rec + (long long)(b * NS + k) * Cfg::THREADS, gr + ch[k] * cs);
+        };
+        if (STAGED) {
+            if (rec_uniform) rec_fetch(k1 - 1, 0);
+            stage_fetch(srec + (long long)((n_stages - 1) * SST) * srow_stride, 0);      // (commits both)
+        }
+#else
+        constexpr bool STAGED = false;
+#endif
         for (int step = k1 - 1; step >= k0; --step, srec -= sstep) {
             if (step < seg_lo) {
                 --seg;
@@ -350,6 +392,17 @@ dps_adjoint_kernel(const PT p) {
             // recorded post-step states: rec[.., step] = x_{step+1}.  Every generator records the same fields in all the
             // usual cases: the field tests are then uniform branches (no divergence bookkeeping); dead lanes read a valid
             // (clamped) address and their co-state is never stored.
+#if DPS_BWD_ASYNC && !DPS_BWD_AOS
+            if (STAGED && rec_uniform) {
+                dps_cp_async_wait<0>();                 // (the first stage of this step needs its record now anyway)
+                const double* cur = s_rec + (long long)rbuf * NS * Cfg::THREADS;
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (rec_mask_u & (1u << k)) lam[k] += cur[k * Cfg::THREADS];
+                if (step > k0) rec_fetch(step - 1, rbuf ^ 1);     // committed with the next stage record
+                rbuf ^= 1;
+            } else
+#endif
             if (rec_uniform) {
                 const double* gr = p.grad_rec + (long long)step * P + s;
 #pragma unroll
@@ -423,19 +476,37 @@ dps_adjoint_kernel(const PT p) {
                     sdi = sds[i]; cdi = cds[i]; vri = vres[i]; vii = vims[i];
                 } else {
                     double rec[SST];
-#if DPS_BWD_AOS
-                    const double2* d2 = reinterpret_cast<const double2*>(srec + i * SST);
+#if DPS_BWD_ASYNC && !DPS_BWD_AOS
+                    if (STAGED) {
+                        if (i > 0 || step > k0) {
+                            const double* nxt = (i > 0) ? srec + (long long)((i - 1) * SST) * srow_stride
+                                                        : srec - sstep + (long long)((n_stages - 1) * SST) * srow_stride;
+                            stage_fetch(nxt, sbuf ^ 1);
+                            dps_cp_async_wait<1>();
+                        } else {
+                            dps_cp_async_wait<0>();
+                        }
+                        const double* cur = s_stage + (long long)sbuf * SST * Cfg::THREADS;
 #pragma unroll
-                    for (int k = 0; k < SST / 2; ++k) {
-                        const double2 v = d2[k];
-                        rec[2 * k] = v.x;
-                        rec[2 * k + 1] = v.y;
-                    }
-#else
-                    const double* d = srec + (long long)(i * SST) * srow_stride;
-#pragma unroll
-                    for (int k = 0; k < NS + 4; ++k) rec[k] = d[k * srow_stride];
+                        for (int k = 0; k < NS + 4; ++k) rec[k] = cur[k * Cfg::THREADS];
+                        sbuf ^= 1;
+                    } else
 #endif
+                    {
+#if DPS_BWD_AOS
+                        const double2* d2 = reinterpret_cast<const double2*>(srec + i * SST);
+#pragma unroll
+                        for (int k = 0; k < SST / 2; ++k) {
+                            const double2 v = d2[k];
+                            rec[2 * k] = v.x;
+                            rec[2 * k + 1] = v.y;
+                        }
+#else
+                        const double* d = srec + (long long)(i * SST) * srow_stride;
+#pragma unroll
+                        for (int k = 0; k < NS + 4; ++k) rec[k] = d[k * srow_stride];
+#endif
+                    }
 #pragma unroll
                     for (int k = 0; k < NS; ++k) Xi[k] = rec[k];
                     sdi = rec[NS]; cdi = rec[NS + 1]; vri = rec[NS + 2]; vii = rec[NS + 3];
@@ -568,10 +639,16 @@ template <class PT, int G, int CM, bool ZGRAD, int SOLVER, int NGP, int PM, bool
 static cudaError_t launch_bwd_one(const PT& p, cudaStream_t stream) {
     using C = BwdCfg<G>;
     const int GG = C::WIDE ? p.n_gen : G;
-    const size_t smem = sizeof(double2) * C::WARPS * 64 + sizeof(double) * GG * DPS_N_SLOTS + sizeof(short) * GG * DPS_N_SLOTS +
-                        ((C::WIDE || p.z_per_sim) ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
+    const size_t smem_tables = sizeof(double2) * C::WARPS * 64 + sizeof(double) * GG * DPS_N_SLOTS + sizeof(short) * GG * DPS_N_SLOTS +
+                               ((C::WIDE || p.z_per_sim) ? 0 : sizeof(double) * 4 * (size_t)p.n_cfg * G * G);
     const long long spb = C::WIDE ? C::THREADS / ((p.n_gen + 31) & ~31) : (long long)C::WARPS * C::SPW;
     const long long blocks = (p.P + spb - 1) / spb;
+    // staging area of the sweep (two stage records per thread, dps_adjoint_kernel), 16-byte aligned behind the tables
+    constexpr int SST = ((CM != 0 ? DPS_N_STATES : 6) + 5) & ~1;
+    const size_t stage_offset = (smem_tables + 15) & ~(size_t)15;
+    const size_t smem = stage_offset + ((DPS_BWD_ASYNC && !DPS_BWD_AOS && !INREG) ? sizeof(double) * 2 * (SST + SST - 4) * C::THREADS : 0);   // + [2][NS] cotangents
+    PT pp = p;
+    pp.stage_offset = (int)stage_offset;
     // The fast-constant builds (no network gradient: those accumulate dL/dZ in HBM across chunks) only exist as work-queue
     // kernels; a launch that is not worth cutting into chunks runs as a queue of one chunk per block group.
     constexpr bool Q = !ZGRAD && (PM != 0);
@@ -581,14 +658,14 @@ static cudaError_t launch_bwd_one(const PT& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
     }
     if constexpr (Q) {
-        PT q = p;
+        PT q = pp;
         unsigned grid = (unsigned)blocks;
         cudaError_t e = plan_adjoint_queue(q, (const void*)kern, C::THREADS, smem, blocks, &grid, stream);
         if (e != cudaSuccess) return e;
         kern<<<grid, C::THREADS, smem, stream>>>(q);
         return cudaGetLastError();
     } else {
-        kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(p);
+        kern<<<(unsigned)blocks, C::THREADS, smem, stream>>>(pp);
         return cudaGetLastError();
     }
 }

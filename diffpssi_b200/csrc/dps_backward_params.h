@@ -27,6 +27,7 @@ struct BwdParamsT {
     int seg_cfg[MAX_SEG];
     int ctrl[MAXG];
     unsigned rec_mask[MAXG];
+    int stage_offset;          // byte offset of the sweep's staging area in dynamic shared memory (set by the launcher)
     int rec_uniform;           // rec_mask identical for every generator (field tests become uniform branches)
     short rec_chan[MAXG][DPS_N_FIELDS];
     short obs_chan[MAX_EXTRA_OBS][2];

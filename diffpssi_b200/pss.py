@@ -262,11 +262,11 @@ class PowerSystemSimulation(object):
         """Checkpoint stride of a run that needs gradients.  ``ckpt_stride`` given by the caller wins.  Otherwise 1 -- the
         state before every step is kept and the adjoint evaluates each step's stages in registers, without re-integration
         or scratch -- for systems of up to 4 generators whose n_steps x n_gen x 13 x P doubles fit a quarter of the free
-        device memory (at most 24 GB); else the shortest of 4, 8, 16, 32 whose checkpoints fit that budget.  With more generators a warp holds few trajectories, its checkpoint stores
+        device memory (at most 24 GB); else the shortest of 8, 16, 32 whose checkpoints fit that budget.  With more generators a warp holds few trajectories, its checkpoint stores
         are 24..48-byte pieces and writing every step costs the forward pass more than the adjoint gains (IEEE-39, 8192
         sims: forward +11 ms).  A short stride keeps the per-segment scratch of the adjoint (every stage's inputs, sin/cos
-        and bus voltage for each step of a segment) near L2 size: IEEE-39, 8192 sims: 26.7 ms per backward pass at stride 4,
-        28.5 ms at 8, 30.4 ms at 16; the forward pass does not notice (profiles/round2/adjoint_r3.txt)."""
+        and bus voltage for each step of a segment) near L2 size: IEEE-39, 8192 sims: 25 ms per backward pass at strides 4 and
+        8, ~27 ms at 16; the forward pass does not notice (profiles/round2/adjoint_r3.txt)."""
         if self.ckpt_stride is not None:
             return int(self.ckpt_stride)
         full = len(self.time) * n_gen * engine.N_STATES * self.parallel_sims * 8
@@ -276,7 +276,7 @@ class PowerSystemSimulation(object):
             budget = min(budget, free / 4)
         if n_gen <= 4 and full <= budget:
             return 1
-        for stride in (4, 8, 16):
+        for stride in (8, 16):
             if full / stride <= budget:
                 return stride
         return 32
