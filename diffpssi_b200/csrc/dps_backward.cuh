@@ -103,6 +103,15 @@ dps_adjoint_kernel(const PT p) {
     short* s_vary = reinterpret_cast<short*>(s_zni + n_cfg_s * G * G);           // [G][DPS_N_SLOTS]
     // staging area of the sweep: [2][SST][THREADS] doubles, one stage record per buffer, a column per thread (see below)
     double* s_stage = reinterpret_cast<double*>(smem_raw + p.stage_offset) + threadIdx.x;
+    // WIDE: the generator block of the ACTIVE fault configuration in shared memory when it fits (re / im planes, row
+    // stride LDZ odd: a warp reads a row segment (V = Z I, lanes = rows) or a column segment (dI = Z^T dV, lanes = columns)
+    // without bank conflicts from the one copy); reloaded when the configuration changes.  It takes the staging area's
+    // place.  Until round 2b both products read Z from L2 (the 100-generator sweep was ~10x the forward pass per step).
+    const bool wide_z = WIDE && p.wide_z_smem;
+    const int LDZ = GG | 1;
+    double* s_zw_re = reinterpret_cast<double*>(smem_raw + p.stage_offset);
+    double* s_zw_im = s_zw_re + GG * LDZ;
+    int z_loaded = -1;
 
     const int lane = WIDE ? (int)threadIdx.x : (int)(threadIdx.x & 31);          // index into the exchange line
     const int warp = threadIdx.x >> 5;
@@ -191,6 +200,19 @@ dps_adjoint_kernel(const PT p) {
     const long long z_col_stride = 2 * zb;                              // (row, col) -> (row, col+1)
     const long long z_row_stride = (long long)p.z_cols * 2 * zb;        // (row, col) -> (row+1, col)
     auto z_cfg = [&](int cfg) { return p.zsub + ((long long)cfg * p.z_rows * p.z_cols * 2) * zb + zs; };
+    auto ensure_z = [&](int cfg) {                    // (block-uniform: every thread of a block walks the same steps)
+        if (WIDE && wide_z && cfg != z_loaded) {
+            __syncthreads();
+            const double* zc = p.zsub + (long long)cfg * p.z_rows * p.z_cols * 2;
+            for (int i = threadIdx.x; i < GG * GG; i += blockDim.x) {
+                const int r = i / GG, c = i - r * GG;
+                s_zw_re[r * LDZ + c] = zc[((long long)r * p.z_cols + c) * 2];
+                s_zw_im[r * LDZ + c] = zc[((long long)r * p.z_cols + c) * 2 + 1];
+            }
+            __syncthreads();
+            z_loaded = cfg;
+        }
+    };
     // one stage evaluation at X: sin/cos, network voltage, derivatives
     auto eval_stage = [&](const double* X, int cfg, double& sd, double& cd, double& v_re, double& v_im, double* f,
                           Algebraics& alg) {
@@ -206,6 +228,16 @@ dps_adjoint_kernel(const PT p) {
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 const double zr = zr_[j * G], zi = zi_[j * G];
+                const double jr = xb[j].x, ji = xb[j].y;
+                v_re += zr * jr - zi * ji;
+                v_im += zr * ji + zi * jr;
+            }
+        } else if (WIDE && wide_z) {
+            const double* zr_ = s_zw_re + g * LDZ;
+            const double* zi_ = s_zw_im + g * LDZ;
+#pragma unroll 4
+            for (int j = 0; j < p.n_gen; ++j) {
+                const double zr = zr_[j], zi = zi_[j];
                 const double jr = xb[j].x, ji = xb[j].y;
                 v_re += zr * jr - zi * ji;
                 v_im += zr * ji + zi * jr;
@@ -299,6 +331,7 @@ dps_adjoint_kernel(const PT p) {
                     cfg = p.seg_cfg[seg];
                     next_change = (seg + 1 < p.n_seg) ? p.seg_step[seg + 1] : 0x7fffffff;
                 }
+                ensure_z(cfg);
 #pragma unroll
                 for (int st = 0; st < n_stages; ++st) {
                     const double* X = (st == 0) ? xs : xt;
@@ -359,7 +392,7 @@ dps_adjoint_kernel(const PT p) {
         // the record the sweep needs next (the previous stage, or the last stage of the previous step) is already on its
         // way from L2, so its latency is off the dependency chain (it was 25 % of the kernel's stall samples).  Every
         // thread copies and reads only its own column: no barrier, cp.async.wait_group orders copy and read.
-        constexpr bool STAGED = !INREG;
+        constexpr bool STAGED = !INREG && !WIDE;
         int sbuf = 0;
         auto stage_fetch = [&](const double* rec_ptr, int b) {
             double* dst = s_stage + (long long)b * SST * Cfg::THREADS;
@@ -389,6 +422,7 @@ dps_adjoint_kernel(const PT p) {
                 cfg = p.seg_cfg[seg];
                 seg_lo = p.seg_step[seg];
             }
+            ensure_z(cfg);
             // recorded post-step states: rec[.., step] = x_{step+1}.  Every generator records the same fields in all the
             // usual cases: the field tests are then uniform branches (no divergence bookkeeping); dead lanes read a valid
             // (clamped) address and their co-state is never stored.
@@ -542,6 +576,16 @@ dps_adjoint_kernel(const PT p) {
                         di_re += zr * ar + zi * ai;
                         di_im += -zi * ar + zr * ai;
                     }
+                } else if (WIDE && wide_z) {
+                    const double* zr_ = s_zw_re + g;
+                    const double* zi_ = s_zw_im + g;
+#pragma unroll 4
+                    for (int r = 0; r < p.n_gen; ++r) {
+                        const double zr = zr_[r * LDZ], zi = zi_[r * LDZ];
+                        const double ar = xb[r].x, ai = xb[r].y;
+                        di_re += zr * ar + zi * ai;
+                        di_im += -zi * ar + zr * ai;
+                    }
                 } else {
                     const double* zp = z_cfg(cfg) + g * z_col_stride;
                     for (int r = 0; r < p.n_gen; ++r, zp += z_row_stride) {
@@ -646,9 +690,15 @@ static cudaError_t launch_bwd_one(const PT& p, cudaStream_t stream) {
     // staging area of the sweep (two stage records per thread, dps_adjoint_kernel), 16-byte aligned behind the tables
     constexpr int SST = ((CM != 0 ? DPS_N_STATES : 6) + 5) & ~1;
     const size_t stage_offset = (smem_tables + 15) & ~(size_t)15;
-    const size_t smem = stage_offset + ((DPS_BWD_ASYNC && !DPS_BWD_AOS && !INREG) ? sizeof(double) * 2 * (SST + SST - 4) * C::THREADS : 0);   // + [2][NS] cotangents
+    size_t smem = stage_offset + ((DPS_BWD_ASYNC && !DPS_BWD_AOS && !INREG && !C::WIDE) ? sizeof(double) * 2 * (SST + SST - 4) * C::THREADS : 0);   // + [2][NS] cotangents
+    int wide_z_smem = 0;
+    if (C::WIDE && !p.z_per_sim && getenv("DPS_BWD_WIDE_Z_GLOBAL") == nullptr) {      // wide: Z of the active configuration instead
+        const size_t zbytes = sizeof(double) * 2 * (size_t)GG * (GG | 1);
+        if (stage_offset + zbytes <= 227 * 1024) { smem = stage_offset + zbytes; wide_z_smem = 1; }
+    }
     PT pp = p;
     pp.stage_offset = (int)stage_offset;
+    pp.wide_z_smem = wide_z_smem;
     // The fast-constant builds (no network gradient: those accumulate dL/dZ in HBM across chunks) only exist as work-queue
     // kernels; a launch that is not worth cutting into chunks runs as a queue of one chunk per block group.
     constexpr bool Q = !ZGRAD && (PM != 0);

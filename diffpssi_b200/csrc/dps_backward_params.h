@@ -27,6 +27,7 @@ struct BwdParamsT {
     int seg_cfg[MAX_SEG];
     int ctrl[MAXG];
     unsigned rec_mask[MAXG];
+    int wide_z_smem;           // wide build: the active configuration's generator block of Z is kept in shared memory
     int stage_offset;          // byte offset of the sweep's staging area in dynamic shared memory (set by the launcher)
     int rec_uniform;           // rec_mask identical for every generator (field tests become uniform branches)
     short rec_chan[MAXG][DPS_N_FIELDS];

@@ -1,5 +1,5 @@
 """Where does an identification step spend its time?  (run on the GPU box)
-    python tools/adjoint_probe.py [ibb|k2a|ieee39] [P]"""
+    [CKPT=<stride>] [SOLVER=rk4] [CELLS=100] python tools/adjoint_probe.py [ibb|k2a|ieee39|tiled] [P]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -8,7 +8,7 @@ from tests import helpers
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'ibb'
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-T = 2000
+T = int(os.environ.get("STEPS", 2000))
 rng = np.random.RandomState(0)
 if which == 'ibb':
     grid, ev = helpers.load_grid('ibb'), (1, 1.05, 'Bus 1')
@@ -20,13 +20,21 @@ elif which == 'k2a':
     for g, (h, x) in grids.GENERATOR_NOMINALS['k2a'].items():
         ov[(g, 'h')] = h * rng.uniform(0.8, 1.25, P); ov[(g, 'd')] = rng.uniform(0, 2, P)
     chans = ['G%d.omega' % i for i in (1, 2, 3, 4)]
+elif which == 'tiled':                           # BASELINE config 5's grid (500 buses / 100 generators): the wide adjoint
+    n_cells = int(os.environ.get('CELLS', 100))
+    grid, ev = grids.tiled(n_cells), (1.0, 1.1, 'A3')
+    ov = {}
+    for c in range(n_cells):
+        ov[('M%d' % c, 'h')] = (6.5 if c % 2 == 0 else 6.175) * rng.uniform(0.8, 1.25, P)
+        ov[('M%d' % c, 'd')] = rng.uniform(0, 2, P)
+    chans = ['M%d.omega' % c for c in range(n_cells)]
 else:
     grid, ev = grids.ieee39(), (1.0, 1.1, 'B16')
     ov = {}
     for g, (h, x) in grids.GENERATOR_NOMINALS['ieee39'].items():
         ov[(g, 'h')] = h * rng.uniform(0.8, 1.25, P); ov[(g, 'd')] = rng.uniform(0, 2, P)
     chans = ['G%d.omega' % i for i in range(1, 11)]
-sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver='heun', grid_data=grid, verbose=False)
+sim = Pss(parallel_sims=P, sim_time=T * 0.005, time_step=0.005, solver=os.environ.get('SOLVER', 'heun'), grid_data=grid, verbose=False)
 sim.add_sc_event(*ev)
 leaves = helpers.apply_overrides(sim, ov, requires_grad=True)
 sim.ckpt_stride = int(os.environ['CKPT']) if 'CKPT' in os.environ else None      # None: Pss picks (1 when it fits)
