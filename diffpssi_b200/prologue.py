@@ -60,6 +60,7 @@ class _Cols(object):
 
     def __init__(self, P, device, cache=None):
         self.P, self.device = P, device
+        self._dev = torch.device(device)
         # id(tensor) -> (tensor, version): tensors already found batch-uniform.  Keeps run() from re-checking (one
         # device sync each) the hundreds of default parameter tensors that never change between runs.
         self.cache = cache if cache is not None else {}
@@ -70,27 +71,28 @@ class _Cols(object):
             dt = dtype or (C128 if isinstance(value, complex) else F64)
             return torch.full((1, 1), value, dtype=dt, device=self.device)
         t = value
-        if t.device != torch.device(self.device):
+        if t.device != self._dev and t.device.type != self._dev.type:
+            t = t.to(self.device)
+        elif t.device != self._dev and self._dev.index is not None and t.device.index != self._dev.index:
             t = t.to(self.device)
         if t.dim() == 0:
             t = t.reshape(1, 1)
         elif t.dim() == 1:
             t = t.reshape(-1, 1)
+        if last_row:
+            t = t[-1:]
+        elif collapse and t.shape[0] == P and P > 1 and not t.requires_grad:
+            # (collapse BEFORE any dtype conversion: converting one row instead of P)
+            hit = self.cache.get(id(value))
+            if (hit is not None and hit[0] is value and hit[1] == value._version) or known_uniform(value):
+                t = t[:1]
+            elif bool((t == t[:1]).all()):
+                self.cache[id(value)] = (value, value._version)
+                t = t[:1]
         if dtype is not None and t.dtype != dtype:
             if t.is_complex() and not dtype.is_complex:
                 t = t.real
             t = t.to(dtype)
-        if last_row:
-            return t[-1:]
-        if collapse and t.shape[0] == P and P > 1 and not t.requires_grad:
-            hit = self.cache.get(id(value))
-            if hit is not None and hit[0] is value and hit[1] == value._version:
-                return t[:1]
-            if known_uniform(value):
-                return t[:1]
-            if bool((t == t[:1]).all()):
-                self.cache[id(value)] = (value, value._version)
-                return t[:1]
         return t
 
 
