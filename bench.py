@@ -77,9 +77,10 @@ def build_sim(P, device, rows, batch_host, variant='headline'):
     import torch
     from diffpssi_b200 import Pss, grids
     sim = Pss(parallel_sims=P, sim_time=T_STEPS * DT, time_step=DT, solver='heun',
-              grid_data=generic_grid() if variant == 'generic' else grids.ieee39(), verbose=False, device=device)
+              grid_data=generic_grid() if variant in ('generic', 'generic-ctrl') else grids.ieee39(), verbose=False, device=device)
     sim.add_sc_event(*FAULT)
-    if variant == 'generic':          # omega AND delta of every generator: the run-time recorder mask, 160 B per sim-step
+    # ('generic-ctrl' / 'generic-rec': only one of the two differences, to see which one costs what)
+    if variant in ('generic', 'generic-rec'):          # omega AND delta of every generator: the run-time recorder mask, 160 B per sim-step
         sim.set_record_function(lambda s: [s.busses[29 + i].models[0].omega.real for i in range(10)] +
                                           [s.busses[29 + i].models[0].delta.real for i in range(10)])
     else:
@@ -286,9 +287,11 @@ def run_reference_arm(args, out=sys.stdout):
 
 
 def kernel_label(info, variant):
-    if variant == 'generic':
-        return ('dps_step_kernel<G=10, all controllers, per-generator controller constants from shared memory, heun, '
-                'run-time recorder mask> (%d registers)' % info['regs_per_thread'])
+    if variant.startswith('generic'):
+        consts = 'constant-bank controller constants' if variant == 'generic-rec' else 'per-generator controller constants from shared memory'
+        rec = 'omega recorder' if variant == 'generic-ctrl' else 'run-time recorder mask'
+        return ('dps_step_pair_kernel<G=10, all controllers, %s, heun, %s> (two trajectories per thread, %d registers)'
+                % (consts, rec, info['regs_per_thread']))
     if info['sims_per_block'] % 6 == 0 and info['regs_per_thread'] > 170:
         return 'dps_step_pair_kernel<G=10, heun, omega recorder> (two trajectories per thread, %d registers)' % info['regs_per_thread']
     return ('dps_step_kernel<G=10, all controllers, constant-bank controller constants, heun> (%d registers)'
@@ -302,7 +305,7 @@ def workload_config(P, n_gpus, note=None, variant='headline', n_rec=10):
            'parameters': "per-sim H, X_d' ~ U(0.5,2) x nominal and D ~ U(0,2) for every generator",
            'l2': 'recorder output (%.1f GB per bench step per GPU) far exceeds the 126 MB L2, so inputs are evicted '
                  'between timed iterations' % (P / n_gpus * T_STEPS * 8 * n_rec / 1e9)}
-    if variant == 'generic':
+    if variant.startswith('generic'):
         cfg['variant'] = ('generic: controller gains / time constants differ per generator (no common-constant kernel '
                           'specialisation, no two-trajectory kernel), recorder = omega and delta of the 10 generators')
     if note:
@@ -513,7 +516,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--sims', type=int, default=P_GLOBAL, help='global parallel_sims (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--variant', default='headline', choices=('headline', 'generic'),
+    ap.add_argument('--variant', default='headline', choices=('headline', 'generic', 'generic-ctrl', 'generic-rec'),
                     help="'generic': distinct controller constants per generator + omega/delta recorder (no specialised kernel)")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--config', default='c3', choices=('c3', 'c4', 'c5'),

@@ -385,14 +385,19 @@ bool try_pair_kernel(const FwdParams& p, int cmask, int pmode, cudaStream_t stre
     const long long min_sims = env ? atoll(env) : 8192;
     if (!pair_kernel_applies<G>(p, cmask, pmode, min_sims)) return false;
     if (spb) *spb = PairCfg<G>::WARPS * PairCfg<G>::SPW * 2;
-    // two builds: the headline specialisation (common constants in the constant bank, omega recorder folded in) and the
-    // general one (per-generator constants from shared memory, run-time recorder mask) for everything else that applies
-    if (pmode == 3 && p.rec_umask == 0x1u)
-        *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN, 0x1, 3>(p, stream, regs)
-                                      : launch_pair_solver<G, DPS_EULER, 0x1, 3>(p, stream, regs);
+    // four builds: controller constants common to all generators in the constant bank (pmode 3) or per generator from shared
+    // memory (pmode 1)  x  the omega recorder folded in at compile time or the run-time recorder mask.  (Until round 2b only the
+    // two corners existed and a grid that differed from the headline in ONE of the two paid for both.)
+    const bool rec_w = (p.rec_umask == 0x1u);
+    const bool heun = (p.solver == DPS_HEUN);
+    if (pmode == 3 && rec_w)
+        *err = heun ? launch_pair_solver<G, DPS_HEUN, 0x1, 3>(p, stream, regs) : launch_pair_solver<G, DPS_EULER, 0x1, 3>(p, stream, regs);
+    else if (pmode == 3)
+        *err = heun ? launch_pair_solver<G, DPS_HEUN, -1, 3>(p, stream, regs) : launch_pair_solver<G, DPS_EULER, -1, 3>(p, stream, regs);
+    else if (rec_w)
+        *err = heun ? launch_pair_solver<G, DPS_HEUN, 0x1, 1>(p, stream, regs) : launch_pair_solver<G, DPS_EULER, 0x1, 1>(p, stream, regs);
     else
-        *err = (p.solver == DPS_HEUN) ? launch_pair_solver<G, DPS_HEUN, -1, 1>(p, stream, regs)
-                                      : launch_pair_solver<G, DPS_EULER, -1, 1>(p, stream, regs);
+        *err = heun ? launch_pair_solver<G, DPS_HEUN, -1, 1>(p, stream, regs) : launch_pair_solver<G, DPS_EULER, -1, 1>(p, stream, regs);
     return true;
 }
 
