@@ -99,8 +99,8 @@ cudaError_t launch_forward_wide(const WideParams& p, int cmask, int pmode, cudaS
                                 int* threads, int* sims_per_block);
 #endif
 
-constexpr int RED_MAX_CFG = 16;      // distinct faulted-bus sets per run
-constexpr int RED_MAX_FAULT = 8;     // simultaneously faulted buses
+constexpr int RED_MAX_CFG = 64;      // distinct faulted-bus sets per run
+constexpr int RED_MAX_FAULT = 16;    // simultaneously faulted buses
 
 struct ReduceParams {
     long long Bz;

@@ -19,8 +19,8 @@ N_FIELDS = 20
 MAX_G = 16          # warp-exchange stepper
 MAX_GW = 128        # wide stepper
 MAX_EXTRA_OBS = 64
-MAX_CFG = 16
-MAX_FAULT = 8
+MAX_CFG = 64
+MAX_FAULT = 16
 
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes', 'dps_forward_workspace_bytes',
            'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_fp64_dmma_probe', 'dps_math_probe', 'dps_plan_info',

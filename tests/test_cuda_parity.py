@@ -535,3 +535,30 @@ def test_work_queue_at_small_batch(monkeypatch, pair_min):
             _, streamed = sim.run(host_out=host, stream_chunks=3)
             assert torch.equal(streamed, res.cpu())
     assert torch.equal(out[None], out['2'])
+
+
+@pytest.mark.parametrize('n_faults', [12, 16])
+def test_many_fault_configurations_against_oracle(n_faults):
+    """More distinct fault configurations (17 > the former cap of 16) and more simultaneously faulted buses (16 > the former 8)
+    than rounds 1-2a accepted.  With the reference's multi-event semantics (simulator.py:524-531: a later inactive event
+    wipes the faults of earlier ones) a growing set needs nested events listed latest-start first; the fault re-reduction
+    applies one rank-1 update per faulted bus, the oracle inverts twice per active step."""
+    from diffpssi_b200 import grids
+    P = 5
+    sim = Pss(parallel_sims=P, sim_time=0.4, time_step=0.005, solver='heun', grid_data=grids.ieee39(), verbose=False)
+    buses = ['B%d' % b for b in range(3, 3 + n_faults)]
+    for k in reversed(range(n_faults)):                      # event k starts at 0.102 + 0.01 k, all end at 0.3
+        sim.add_sc_event(0.102 + 0.01 * k, 0.3, buses[k])
+    rng = np.random.RandomState(8)
+    ov = {}
+    for g, (h, x) in grids.GENERATOR_NOMINALS['ieee39'].items():
+        ov[(g, 'h')] = h * rng.uniform(0.9, 1.1, P)
+    helpers.apply_overrides(sim, ov)
+    sim.set_record_channels(['G%d.%s' % (i, f) for i in range(1, 11) for f in ('omega', 'delta', 'e_q_st', 'p_e')])
+    _, res = sim.run()
+    assert sim.last_plan.topo['n_cfg'] == n_faults + 1
+    ref = helpers.run_oracle_for(sim, sim.last_init)
+    idx = [helpers.oracle.FIELD_NAMES.index(f) for f in ('omega', 'delta', 'e_q_st', 'p_e')]
+    want = ref['full'][:, :, idx, :].transpose(3, 0, 1, 2).reshape(P, len(sim.time), -1)
+    err = np.abs(res.cpu().numpy() - want).max()
+    assert err < TOL, err
