@@ -17,8 +17,9 @@ def wanted_slots(init, slot_names):
     return want
 
 
-def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec, want_z=False):
-    """-> (g_x0 [G,13,P], g_upar [G,N_SLOTS], g_vpar [n_vary,P] or None, g_zsub like zsub or None)."""
+def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec, want_z=False, g_xf=None):
+    """-> (g_x0 [G,13,P], g_upar [G,N_SLOTS], g_vpar [n_vary,P] or None, g_zsub like zsub or None).
+    ``g_xf`` [G,13,P]: cotangent of the final state (a later step range's g_x0), or None."""
     engine.require_cuda()
     lib = plan.lib
     topo = plan.topo
@@ -37,7 +38,7 @@ def run_backward(plan, P, upar, vpar, zsub, ckpt, g_rec, want_z=False):
     with engine._on_device_of(ckpt):
         rc = lib.dps_backward(plan.handle, P, engine._ptr(upar.detach().contiguous()),
                               engine._ptr(vpar.detach().contiguous()) if vpar is not None else None,
-                              engine._ptr(zsub), engine._ptr(ckpt), engine._ptr(g_rec), None, a_want,
+                              engine._ptr(zsub), engine._ptr(ckpt), engine._ptr(g_rec), engine._ptr(g_xf), a_want,
                               engine._ptr(g_x0), engine._ptr(gslot), engine._ptr(gz),
                               ctypes.c_void_p(ws.data_ptr()), ws_bytes, engine._stream(ckpt))
     engine._check(lib, rc, 'dps_backward')

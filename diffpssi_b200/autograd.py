@@ -30,7 +30,10 @@ class StepFunction(torch.autograd.Function):
         ctx.has_vpar = vpar is not None
         ctx.save_for_backward(upar, vpar if vpar is not None else upar, zsub, ckpt if ckpt is not None else upar)
         ctx.has_ckpt = ckpt is not None
-        ctx.mark_non_differentiable(x_final)
+        ctx.rec_shape = tuple(rec.shape)
+        # x_final is differentiable: a run that is cut into step ranges (parameter events) chains the final state of one
+        # range into the initial state of the next, and the co-state travels back the same way (dps_backward: grad_x_final)
+        ctx.set_materialize_grads(False)
         return rec, x_final
 
     @staticmethod
@@ -39,6 +42,9 @@ class StepFunction(torch.autograd.Function):
         upar, vpar, zsub, ckpt = ctx.saved_tensors
         if not ctx.has_ckpt:
             raise engine.EngineError('backward needs checkpoints: run() saw no tensor requiring grad')
+        if g_rec is None:
+            g_rec = torch.zeros(ctx.rec_shape, dtype=torch.float64, device=upar.device)
         g_x0, g_upar, g_vpar, g_zsub = run_backward(ctx.plan, ctx.P, upar, vpar if ctx.has_vpar else None, zsub, ckpt,
-                                                    g_rec.contiguous(), want_z=ctx.needs_input_grad[5])
+                                                    g_rec.contiguous(), want_z=ctx.needs_input_grad[5],
+                                                    g_xf=None if g_xf is None else g_xf.contiguous())
         return None, None, g_x0, g_upar, g_vpar, g_zsub

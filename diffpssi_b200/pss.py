@@ -406,7 +406,61 @@ class PreparedRun(object):
                 self.reduce_network()
             zsub = self.zsub
         rec, x_final = StepFunction.apply(self.plan, self.sim.parallel_sims, self.x0, self.upar, self.vpar, zsub)
-        return self._assemble(rec), x_final
+        return self._assemble(rec), x_final.detach()
+
+    def _needs_grad(self):
+        topo = self.topo
+        return torch.is_grad_enabled() and (topo.get('ckpt_stride', 0) > 0 or topo.get('want_z') or self.x0.requires_grad or
+                                            self.upar.requires_grad or (self.vpar is not None and self.vpar.requires_grad))
+
+    def execute_ranges_grad(self, param_events):
+        """Parameter events WITH gradients: every step range between two events is its own plan (its slice of the fault
+        schedule, its constants, its checkpoints) and its own node of the autograd graph; the final state of a range is the
+        differentiable initial state of the next, so the co-state travels back through the events exactly as torch
+        autograd carries it through the reference's loop (a parameter that an event overwrites only collects the gradient
+        of the steps before the event)."""
+        engine.require_cuda()
+        sim, topo = self.sim, self.topo
+        P, T, dev = sim.parallel_sims, topo['n_steps'], sim.device
+        cuts, when = {0, T}, {}
+        for ev in param_events:
+            hit = [k for k, t in enumerate(sim.time) if t >= ev.start_time]      # ParamEvent.handle_event: t >= start
+            if hit:
+                cuts.add(hit[0])
+                when.setdefault(hit[0], []).append(ev)
+        cuts = sorted(cuts)
+        if topo.get('want_z'):
+            zsub = planning.network_reduce_torch(self.init.Z0, self.init.Ydiag, self.extras['obs_bus'],
+                                                 self.extras['gen_bus'], self.extras['cfg_sets'], self.extras['m_max']).to(dev)
+        else:
+            with torch.no_grad():
+                self.reduce_network()
+            zsub = self.zsub
+        stride = topo.get('ckpt_stride', 0) or sim._checkpoint_stride(topo['n_gen'])
+        x_cur, upar, vpar = self.x0, self.upar, self.vpar
+        slot_vary, want, common = topo['slot_vary'], topo.get('want'), topo.get('common_ctrl')
+        if want is None:
+            want = adjoint.wanted_slots(self.init, prologue.SLOTS)
+        recs = []
+        for k0, k1 in zip(cuts[:-1], cuts[1:]):
+            if k0 in when:
+                for ev in when[k0]:
+                    setattr(ev.model, ev.param_name, ev.value)
+                    ev.handled = True
+                saved = self.init.slots
+                self.init.slots = prologue.refresh_loop_slots(sim, self.init, sim.prologue_device)
+                try:
+                    upar, vpar, slot_vary = planning.pack_slots(self.init, P, sim.prologue_device)
+                    want = adjoint.wanted_slots(self.init, prologue.SLOTS)
+                    common = planning.common_controller_constants(self.init, upar, slot_vary)
+                finally:
+                    self.init.slots = saved
+                upar, vpar = upar.to(dev), None if vpar is None else vpar.to(dev)
+            t_r = dict(topo, n_steps=k1 - k0, step_cfg=list(topo['step_cfg'][k0:k1]), slot_vary=slot_vary,
+                       n_vary=0 if vpar is None else vpar.shape[0], ckpt_stride=stride, want=want, common_ctrl=common)
+            rec_r, x_cur = StepFunction.apply(engine.Plan(t_r), P, x_cur, upar, vpar, zsub)
+            recs.append(rec_r)
+        return self._assemble(torch.cat(recs, dim=1)), x_cur.detach()
 
     def _assemble(self, rec):
         rows = self.extras['key_rows']
@@ -423,15 +477,17 @@ class PreparedRun(object):
           is re-initialised and Z is not rebuilt;
         * **streaming the recorder to the host**: each finished range is copied to ``host_out`` on a second stream while
           the next range is being integrated.
-        No autograd through this path."""
+        Parameter events with gradients go through :meth:`execute_ranges_grad`; a streamed run carries no autograd."""
         engine.require_cuda()
         sim, topo = self.sim, self.topo
-        if torch.is_grad_enabled() and (topo.get('ckpt_stride', 0) > 0 or topo.get('want_z') or self.x0.requires_grad or
-                                        self.upar.requires_grad or (self.vpar is not None and self.vpar.requires_grad)):
+        if self._needs_grad():
             # ckpt_stride > 0 <=> prepare() saw a tensor requiring grad (a model parameter, or a network parameter that
-            # reaches Z0 / Ydiag); ranges carry no autograd graph, so refuse instead of returning a detached result
-            raise NotImplementedError('gradients through parameter events / streamed runs are not supported: wrap run() '
-                                      'in torch.no_grad() or drop requires_grad')
+            # reaches Z0 / Ydiag)
+            if host_out is None:
+                return self.execute_ranges_grad(param_events)
+            # the streamed ranges carry no autograd graph: refuse instead of returning a detached result
+            raise NotImplementedError('gradients through a run streamed to the host are not supported: wrap run() in '
+                                      'torch.no_grad() or drop requires_grad')
         P, T, dev = sim.parallel_sims, topo['n_steps'], sim.device
         cuts = {0, T}
         when = {}

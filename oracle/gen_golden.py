@@ -200,7 +200,7 @@ def grad_cases(sel):
     import torch
     rng = np.random.RandomState(1)
 
-    def one(name, gname, P, solver, sim_time, events, ov, chans, fd_check):
+    def one(name, gname, P, solver, sim_time, events, ov, chans, fd_check, pev=None):
         if sel and not any(s in name for s in sel):
             return
         grid = rh.load_example_grid(*GRIDS[gname])
@@ -208,7 +208,7 @@ def grad_cases(sel):
         all_names = list(ref_traj['names'])
 
         def run(ovv, grad):
-            sim, leaves = rh.build(grid, P, solver, DT, sim_time, events, ovv, requires_grad=grad)
+            sim, leaves = rh.build(grid, P, solver, DT, sim_time, events, ovv, requires_grad=grad, param_events=pev)
             t, rec, names, snap, rec_t = rh.run_full(sim)
             idx = [names.index(c) for c in chans]
             return sim, leaves, rec_t[:, :, idx], names, snap, t, rec
@@ -226,6 +226,8 @@ def grad_cases(sel):
         extra['loss'] = loss.detach().numpy()
         extra['loss_channels'] = np.array(chans)
         extra['target'] = target[0, :, 0].numpy()
+        if pev:
+            extra['param_events'] = np.array(json.dumps([[t_, '|'.join(p_[1:]), v_] for t_, p_, v_ in pev]))
         # finite-difference cross-check of the oracle's own gradients (one parameter, all sims at once: rows
         # are independent so a simultaneous perturbation of every row gives every row's derivative)
         if fd_check:
@@ -258,6 +260,15 @@ def grad_cases(sel):
         {('gen', 'Gen 1', 'h'): 3.5 * rng.uniform(0.8, 1.5, P),
          ('gen', 'Gen 1', 't_d0_t'): 8.0 * rng.uniform(0.8, 1.25, P)},
         ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], False)
+    # gradients THROUGH parameter events (static_models.py:52-95): D is overwritten at t = 1.0 (its leaf only sees the first
+    # second), H at t = 1.5; X_d' keeps its leaf for the whole run
+    rng_pe = np.random.RandomState(11)           # (its own stream: the cases below keep their draws)
+    one('grad_ibb_param_event_heun', 'ibb', P, 'heun', 2.5, [(0.5, 0.55, 'Bus 1')],
+        {('gen', 'Gen 1', 'h'): 3.5 * rng_pe.uniform(0.8, 1.5, P),
+         ('gen', 'Gen 1', 'd'): rng_pe.uniform(0.5, 2.0, P),
+         ('gen', 'Gen 1', 'x_d_t'): 0.3 * rng_pe.uniform(0.8, 1.25, P)},
+        ['Gen 1.omega', 'Gen 1.e_q_st', 'Gen 1.e_d_st'], True,
+        pev=[(1.0, ('gen', 'Gen 1', 'd'), 2.0), (1.5, ('gen', 'Gen 1', 'h'), 5.0)])
     P = 3
     # H_lim is raised to 0.3 so the PSS works in its linear range part of the time (with the stock 0.03 it is
     # clamped for the whole post-fault window and every PSS gradient is exactly zero).

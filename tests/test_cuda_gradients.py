@@ -145,3 +145,20 @@ def test_adjoint_work_queue_matches_static_launch(monkeypatch, stride):
         ref = np.tile(gold['grad/gen|%s|%s' % k], 40)
         mine = grads['2'][k].cpu().numpy().reshape(-1)
         assert (np.abs(mine - ref) / np.abs(ref).max()).max() < 1e-6
+
+
+@pytest.mark.parametrize('stride', [None, 7])
+def test_adjoint_through_parameter_events(stride):
+    """Gradients THROUGH ParamEvents (static_models.py:52-95): the run is cut at the event steps, every range is its own
+    autograd node and the co-state is handed from one range's adjoint to the previous one's (dps_backward: grad_x_final).
+    Golden: the reference's own autograd on the same run (D overwritten at t = 1.0, H at t = 1.5; FD-checked there)."""
+    sim, gold, leaves = helpers.sim_from_gold('grad_ibb_param_event_heun', 'ibb', device='cuda', requires_grad=True)
+    sim.ckpt_stride = stride
+    names = [str(s) for s in gold['names']]
+    _, result = sim.run()
+    loss = loss_of(result.cpu(), gold, names)
+    assert np.allclose(loss.detach().numpy(), gold['loss'], rtol=1e-9, atol=0)
+    loss.sum().backward()
+    assert_gradients_match(gold, leaves, to_numpy=lambda t: t.cpu().numpy())
+    # the leaf of D stops collecting gradient at its event: compare with an event-free run of the same leaves
+    assert np.abs(leaves[('Gen 1', 'd')].grad.real.cpu().numpy()).max() > 0
