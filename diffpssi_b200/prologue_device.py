@@ -18,7 +18,6 @@ Agreement with the torch prologue: <= 1e-12 on every state, constant and matrix 
 dense solves pivot like LAPACK but sum in a different order.
 """
 import ctypes
-import math
 
 import torch
 

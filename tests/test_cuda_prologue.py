@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from diffpssi_b200 import Pss, grids, planning, prologue
+from diffpssi_b200 import Pss, grids, planning
 from tests import helpers
 from tests.test_cuda_parity import _random_overrides
 
