@@ -199,8 +199,9 @@ def _network_of(sim, cache, dev):
 
 
 def applicable(sim, device):
-    """The kernel path handles networks of up to MAX_BUS buses on a CUDA device."""
-    if not (str(device).startswith('cuda') and 1 <= len(sim.busses) <= MAX_BUS and getattr(sim, 'prologue_kernels', True)):
+    """The kernel path runs on a CUDA device.  (Networks of more than MAX_BUS buses keep torch's batched LU for the load flow
+    and the inverse -- their dense workspaces do not fit shared memory -- and take the model-initialisation kernel.)"""
+    if not (str(device).startswith('cuda') and len(sim.busses) >= 1 and getattr(sim, 'prologue_kernels', True)):
         return False
     # dps_load_flow synchronises the stream once per Newton iteration: not inside a CUDA-graph capture
     return not torch.cuda.is_current_stream_capturing()
@@ -282,16 +283,20 @@ def initialize(sim, device):
             v_init = _cat_cols([col(b.voltage, C128) for b in sim.busses]).contiguous()
             Bs, Bv = s_soll.shape[0], v_init.shape[0]
             B = max(y_static.shape[0], Bs, Bv)
-            V = torch.empty((B, n), dtype=C128, device=dev)
-            s_calc = torch.empty((B, n), dtype=C128, device=dev)
-            worst = torch.zeros(1, dtype=F64, device=dev)
-            it = ctypes.c_int32(0)
-            rc = lib.dps_load_flow(n, bus_type, B, ptr(y_static), y_static.shape[0], ptr(s_soll), Bs, ptr(v_init), Bv,
-                                   ptr(V), ptr(s_calc), ptr(worst), 1e-8, 600, ctypes.byref(it), stream)
-            if rc == 4:
-                raise ValueError('Load flow did not converge')
-            engine._check(lib, rc, 'dps_load_flow')
-            iters = int(it.value)
+            if n <= MAX_BUS:
+                V = torch.empty((B, n), dtype=C128, device=dev)
+                s_calc = torch.empty((B, n), dtype=C128, device=dev)
+                worst = torch.zeros(1, dtype=F64, device=dev)
+                it = ctypes.c_int32(0)
+                rc = lib.dps_load_flow(n, bus_type, B, ptr(y_static), y_static.shape[0], ptr(s_soll), Bs, ptr(v_init), Bv,
+                                       ptr(V), ptr(s_calc), ptr(worst), 1e-8, 600, ctypes.byref(it), stream)
+                if rc == 4:
+                    raise ValueError('Load flow did not converge')
+                engine._check(lib, rc, 'dps_load_flow')
+                iters = int(it.value)
+            else:                           # large network: torch's batched dense solve (same iteration, prologue.load_flow)
+                V, s_calc, iters = prologue.load_flow(sim, col, y_static)
+                V, s_calc = V.contiguous(), s_calc.contiguous()
             cache.pop('dyn_dev', None)
             cache['lf_dev'] = {'key': lf_key, 'keep': lf_keep, 'out': (V, s_calc, iters)}
         res.lf_iters, res.s_calc, res.bus_v = iters, s_calc, V
@@ -315,11 +320,20 @@ def initialize(sim, device):
             y_load = torch.empty((Bd, max(nl, 1)), dtype=C128, device=dev)
             ydiag = torch.empty((Bd, n), dtype=C128, device=dev)
             z0 = torch.empty((Bd, n, n), dtype=C128, device=dev)
-            rc = lib.dps_dynamic_inverse(n, Bd, ptr(y_base), y_base.shape[0], nl, load_bus, ptr(s_load), Bl, ptr(V),
-                                         V.shape[0], ptr(y_load), ptr(ydiag), ptr(z0), stream)
-            engine._check(lib, rc, 'dps_dynamic_inverse')
+            if n <= MAX_BUS:
+                rc = lib.dps_dynamic_inverse(n, Bd, ptr(y_base), y_base.shape[0], nl, load_bus, ptr(s_load), Bl, ptr(V),
+                                             V.shape[0], ptr(y_load), ptr(ydiag), ptr(z0), stream)
+                engine._check(lib, rc, 'dps_dynamic_inverse')
+                y_load = y_load[:max(Bl, V.shape[0])]       # a load's admittance only depends on its own data and on V
+            else:                           # large network: static_models.py:525-527 vectorised, torch.linalg.inv
+                y_dyn = y_base
+                if nl:
+                    v_l = V[:, [bi for bi, _ in loads]]
+                    y_load = 1 / torch.conj(torch.abs(v_l) ** 2 / s_load)
+                    y_dyn = y_base + torch.diag_embed(y_load @ net.inc_load)
+                ydiag = torch.diagonal(y_dyn, dim1=1, dim2=2).contiguous()
+                z0 = torch.linalg.inv(y_dyn)
             res.Ydiag, res.Z0 = ydiag, z0
-            y_load = y_load[:max(Bl, V.shape[0])]           # a load's admittance only depends on its own data and on V
             cache['dyn_dev'] = {'key': dyn_key, 'keep': dyn_keep, 'out': (y_load, ydiag, z0)}
         for li, (_, m) in enumerate(loads):
             m.y_load = y_load[:, li:li + 1]

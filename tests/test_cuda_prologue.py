@@ -34,6 +34,9 @@ def _overrides(grid, P, kind):
             ov[(g, 'd')] = rng.uniform(0, 2, P)
             ov[(g, 'x_d_t')] = x * rng.uniform(0.8, 1.25, P)
         return ov
+    if grid.startswith('tiled'):                # 100 buses: torch LF / inverse + the model-initialisation kernel
+        return {('M0', 'h'): 6.5 * rng.uniform(0.8, 1.25, P), ('M1', 'd'): rng.uniform(0, 2, P),
+                ('M2', 'x_d_t'): 0.3 * rng.uniform(0.8, 1.25, P), ('M3', 'exciter.pt1_lim.gain_pt1'): 100.0 * rng.uniform(0.8, 1.25, P)}
     ov = _random_overrides(grid, P, rng, 0.8, 1.25)
     if kind == 'network':                       # a per-trajectory network: x_d'' enters Y_dyn, a controller constant too
         first = sorted({k[0] for k in ov})[0]
@@ -52,7 +55,7 @@ def _compare(a, b, what, tol=TOL):
 @pytest.mark.parametrize('grid,P,kind', [
     ('ibb', 1, 'uniform'), ('ibb', 33, 'persim'), ('ibb_wc', 70, 'persim'), ('ibb_wc', 40, 'network'),
     ('ieee9', 1, 'uniform'), ('ieee9', 97, 'persim'), ('k2a', 200, 'persim'), ('k2a', 64, 'network'),
-    ('ieee39', 3, 'uniform'), ('ieee39', 512, 'persim'),
+    ('ieee39', 3, 'uniform'), ('ieee39', 512, 'persim'), ('tiled20', 24, 'persim'),
 ])
 def test_kernel_prologue_equals_torch_prologue(grid, P, kind):
     ov = _overrides(grid, P, kind)
