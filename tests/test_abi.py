@@ -91,3 +91,25 @@ def test_integration_doc_struct_matches_the_binding():
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
     assert re.findall(r'(\w+)\s*;', body) == [n for n, _ in mine]
     assert 'DPS_ABI_VERSION = %d' % engine.ABI_VERSION in doc
+
+
+def test_prologue_entry_points_validate_their_arguments():
+    """dps_load_flow / dps_dynamic_inverse / dps_model_init (initialize() on the device): argument errors are return codes
+    with a message, before any CUDA call (so this runs without a GPU); rc 2 = outside the supported size."""
+    import ctypes
+    from diffpssi_b200 import prologue_device
+    lib = engine.load_library()
+    prologue_device._bind(lib)
+    i32 = ctypes.c_int32
+    types = (i32 * 70)(*([0] + [2] * 69))
+    it = i32(0)
+    assert lib.dps_load_flow(65, types, 1, None, 1, None, 1, None, 1, None, None, None, 1e-8, 10, ctypes.byref(it), None) == 2
+    assert b'65 buses' in lib.dps_last_error()
+    assert lib.dps_load_flow(3, types, 1, None, 1, None, 1, None, 1, None, None, None, 1e-8, 10, ctypes.byref(it), None) == 1
+    assert lib.dps_dynamic_inverse(80, 1, None, 1, 0, None, None, 1, None, 1, None, None, None, None) == 2
+    assert lib.dps_dynamic_inverse(5, 1, None, 1, 0, None, None, 1, None, 1, None, None, None, None) == 1
+    zero = (i32 * 4)(0, 0, 0, 0)
+    assert lib.dps_model_init(0, 5, 1, zero, zero, None, 1, None, 1, None, zero, None, None, None, None, None) == 2
+    assert lib.dps_model_init(2, 5, 1, zero, zero, None, 1, None, 1, None, zero, None, None, None, None, None) == 1
+    assert b'bad argument' in lib.dps_last_error()
+    assert prologue_device.N_RAW == 35 and len(prologue_device.RAW) == prologue_device.N_RAW
