@@ -113,3 +113,18 @@ def test_prologue_entry_points_validate_their_arguments():
     assert lib.dps_model_init(2, 5, 1, zero, zero, None, 1, None, 1, None, zero, None, None, None, None, None) == 1
     assert b'bad argument' in lib.dps_last_error()
     assert prologue_device.N_RAW == 35 and len(prologue_device.RAW) == prologue_device.N_RAW
+
+
+def test_raw_parameter_order_matches_header():
+    """enum dps_raw of include/dps.h and prologue_device.RAW (the host-side table builder) list the same parameters in the
+    same order."""
+    import os
+    from diffpssi_b200 import prologue_device as pd
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'dps.h')).read()
+    body = hdr[hdr.index('enum dps_raw {') + len('enum dps_raw {'):hdr.index('DPS_N_RAW\n};')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = [n.split('=')[0].strip() for n in body.split(',') if n.strip()]
+    short = {'sn': 's_n', 'sn_sys': 's_n_sys', 'xd': 'x_d', 'xq': 'x_q', 'xdt': 'x_d_t', 'xqt': 'x_q_t', 'xdst': 'x_d_st',
+             'xqst': 'x_q_st', 'td0t': 't_d0_t', 'tq0t': 't_q0_t', 'td0st': 't_d0_st', 'tq0st': 't_q0_st'}
+    mine = [short.get(n[len('DPS_RAW_'):].lower(), n[len('DPS_RAW_'):].lower()) for n in names]
+    assert mine == list(pd.RAW)
