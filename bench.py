@@ -314,7 +314,7 @@ def workload_config(P, n_gpus, note=None, variant='headline', n_rec=10):
 
 
 C4_SIMS = 16384
-E2E_CHUNKS = 32         # the last slice's copy cannot overlap anything: 1/32 of the output (6 ms at PCIe rate for N = 1)
+E2E_CHUNKS = int(os.environ.get("DPS_E2E_CHUNKS", 32))      # time slices of the streamed recorder copy (A/B: profiles/round2/README.md)
 
 
 def run_c4(args, real_stdout):

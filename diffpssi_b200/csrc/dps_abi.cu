@@ -293,6 +293,28 @@ int dps_network_reduce(int64_t Bz, int32_t n_bus, const double* z_re, const doub
     return 0;
 }
 
+int dps_recorder_to_host(double* host, const double* rec, int32_t n_rows, int64_t row_elems, int64_t first, int64_t count,
+                         void* stream) {
+    if (!host || !rec || n_rows < 1 || row_elems < 1 || first < 0 || count < 1 || first + count > row_elems) {
+        set_error("dps_recorder_to_host: bad argument");
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pitch = sizeof(double) * (size_t)row_elems;
+    cudaError_t e = cudaSuccess;
+    if (pitch <= ((size_t)1 << 31) - 1) {
+        // one strided copy for the time slice of every channel (rows of rec[n_rows][T][P]) instead of one copy per channel
+        e = cudaMemcpy2DAsync(host + first, pitch, rec + first, pitch, sizeof(double) * (size_t)count, (size_t)n_rows,
+                              cudaMemcpyDeviceToHost, st);
+    } else {
+        for (int r = 0; r < n_rows && e == cudaSuccess; ++r)
+            e = cudaMemcpyAsync(host + (size_t)r * row_elems + first, rec + (size_t)r * row_elems + first,
+                                sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, st);
+    }
+    if (e != cudaSuccess) { set_error("dps_recorder_to_host: %s", cudaGetErrorString(e)); return 3; }
+    return 0;
+}
+
 int dps_math_probe(int64_t n, const double* a, const double* b, double* out, void* stream) {
     if (n < 1 || !a || !b || !out) { set_error("dps_math_probe: bad argument"); return 1; }
     cudaError_t e = launch_math_probe(n, a, b, out, (cudaStream_t)stream);

@@ -25,7 +25,7 @@ MAX_FAULT = 16
 EXPORTS = ('dps_plan_create', 'dps_plan_destroy', 'dps_n_checkpoints', 'dps_workspace_bytes', 'dps_forward_workspace_bytes',
            'dps_network_reduce', 'dps_forward', 'dps_forward_range', 'dps_backward', 'dps_fp64_peak_probe', 'dps_fp64_dmma_probe', 'dps_math_probe', 'dps_plan_info',
            'dps_last_error', 'dps_abi_version', 'dps_ident_loss_workspace_bytes', 'dps_ident_loss', 'dps_bfgs_step',
-           'dps_ident_control', 'dps_load_flow', 'dps_dynamic_inverse', 'dps_model_init')
+           'dps_ident_control', 'dps_load_flow', 'dps_dynamic_inverse', 'dps_model_init', 'dps_recorder_to_host')
 
 SOLVER_ID = {'euler': 0, 'heun': 1, 'rk4': 2}
 CH_GEN, CH_BUS_VRE, CH_BUS_VIM = 0, 1, 2
@@ -76,6 +76,8 @@ def load_library(path=None):
     lib.dps_plan_destroy.argtypes = [vp]
     lib.dps_n_checkpoints.argtypes = [vp]
     lib.dps_n_checkpoints.restype = i64
+    lib.dps_recorder_to_host.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+    lib.dps_recorder_to_host.restype = i32
     lib.dps_workspace_bytes.argtypes = [vp, i64]
     lib.dps_workspace_bytes.restype = ctypes.c_size_t
     lib.dps_network_reduce.argtypes = [i64, i32, vp, vp, vp, vp, i32, ctypes.POINTER(i32), i32, ctypes.POINTER(i32),

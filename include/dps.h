@@ -302,6 +302,13 @@ int dps_model_init(int32_t n_gen, int32_t n_bus, int64_t B, const int32_t* gen_b
                    int64_t Bv, const double* s, int64_t Bs, const double* raw_u, const int32_t* raw_vary, const double* raw_v,
                    double* x0, double* slots, double* inj, void* stream);
 
+/* dps_recorder_to_host: the time slice [first, first + count) (in elements: step * P .. ) of every row of the recorder
+ * rec[n_rows][row_elems = T * P] to the same place of a pinned HOST buffer of the same shape, as ONE strided asynchronous
+ * copy (the reference keeps its recorder on the host: simulator.py:540-546).  Used to stream finished step ranges to the
+ * host while later steps are still being integrated (Pss.run(host_out=...)).                                          */
+int dps_recorder_to_host(double* host, const double* rec, int32_t n_rows, int64_t row_elems, int64_t first, int64_t count,
+                         void* stream);
+
 /* Measurement helper: runs a dependent-chain-free DFMA loop on every SM and returns the achieved fp64
  * TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises.  Used by bench.py as the fp64 roofline denominator
  * (MEASURED_PEAKS.json has no fp64 entry). */
